@@ -1,0 +1,199 @@
+/*
+ * yolo_b200.h — C-ABI of libyolo_b200.so: the per-box detection hot path of
+ * KhaledSharif/yolo-from-scratch as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI of its own (it is pure Python on PyTorch); each entry point below
+ * replaces one Python-level function of reference `train.py` (cited as file:line) and is what a
+ * ctypes binding in that file would call.  INTEGRATION.md shows the binding.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a CALLER-OWNED DEVICE pointer unless the name ends in `_host`;
+ *     the library never allocates, frees or retains memory;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream); no entry point synchronises the device or the stream;
+ *   - return value 0 = success, otherwise a cudaError_t or a negative YB_E* code;
+ *     yb_last_error() returns a thread-local, human readable message for the last failure;
+ *   - head tensors use the model-output layout of train.py:608-609: contiguous fp32
+ *     (B, H, W, A, 5+nc), row = [tx, ty, tw, th, obj, cls...] raw logits;
+ *   - `anchors` are fp32 (A,2) = [w,h] in pixels (train.py:372-374, 386-388);
+ *   - tensors must be 16-byte aligned (every torch allocation is).
+ */
+#ifndef YOLO_B200_H
+#define YOLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YB_MAX_SCALES 4
+#define YB_MAX_ANCHORS 8
+
+#define YB_EINVAL (-1)   /* bad argument (shape, null pointer, alignment) */
+#define YB_EWORKSPACE (-2) /* workspace too small */
+
+/* Library/ABI version (major*100+minor) and last error text (thread local). */
+int yb_version(void);
+const char* yb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a-1  decode_predictions(raw_preds, anchors, img_size=640)            train.py:712-779
+ *   out[...,0] = ((2*sigmoid(tx) - 0.5) + gx) / W        (:758)
+ *   out[...,1] = ((2*sigmoid(ty) - 0.5) + gy) / H        (:759)
+ *   out[...,2] = (aw/img) * (2*sigmoid(tw))^2            (:773)
+ *   out[...,3] = (ah/img) * (2*sigmoid(th))^2            (:774)
+ *   out[...,4:] = pred[...,4:]                            (:737, clone)
+ * yb_decode_bwd is its vector-Jacobian product: grad_in = J^T grad_out (autograd of the above).
+ * ---------------------------------------------------------------------------------------- */
+int yb_decode_fwd(const float* pred, const float* anchors, float* out,
+                  int B, int H, int W, int A, int nc, float img_size, void* stream);
+int yb_decode_bwd(const float* pred, const float* anchors, const float* grad_out, float* grad_in,
+                  int B, int H, int W, int A, int nc, float img_size, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a-2  ciou_loss(pred_boxes, target_boxes, eps=1e-7)                    train.py:634-710
+ *   boxes are (N,4) xywh.  loss_out[0] = mean_i(1 - CIoU_i)  (NaN when N == 0, like torch).
+ *   grad_pred / grad_tgt (nullable) receive d loss / d box (alpha is a constant, :701-702).
+ *   `partials` is a caller-provided scratch of yb_ciou_scratch_bytes(N) bytes.
+ * ---------------------------------------------------------------------------------------- */
+size_t yb_ciou_scratch_bytes(long long N);
+int yb_ciou_fwd_bwd(const float* pred_boxes, const float* tgt_boxes, long long N, float eps,
+                    float* loss_out, float* grad_pred, float* grad_tgt,
+                    void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a-3 / a-4  yolo_loss (train.py:781-838) and yolo_loss_multiscale (train.py:840-886),
+ *            forward and backward fused.
+ *
+ * Stage 1  yb_loss_partials: one pass over every scale.
+ *   For each scale s it accumulates partials[s] = { sum_pos(1-CIoU), n_pos, sum_all BCE(obj),
+ *   sum_pos,cls BCE(cls) } (4 doubles per scale) over the LOCAL batch, and when grad[s] != NULL
+ *   writes the dense gradient: the objectness column fully normalised by
+ *   coef_obj[s] / (B_global*H*W*A), box/class columns of positive rows UN-normalised, zeros
+ *   elsewhere.  Positive = target objectness > 0.5 (:809).  Decode uses `img_size` (the
+ *   reference always passes its default 640 here, :796).
+ * Between the stages a data-parallel caller all-reduces(sum) the S*4 doubles.
+ * Stage 2  yb_loss_finalize: takes the (globally reduced) partials, scales the box/class
+ *   gradient entries of the local positive rows by coef_box[s]/P_s and coef_cls[s]/(P_s*nc),
+ *   and writes out4 = { total, sum_s bbox_s, sum_s obj_s, sum_s cls_s } plus, if per_scale != NULL,
+ *   per_scale[s] = { bbox_s, obj_s, cls_s } (means, exactly the three values yolo_loss returns).
+ *   total = sum_s (w_box*bbox_s + w_obj[s]*obj_s + w_cls*cls_s)   (:836, :879).
+ *
+ * coef_* are d(final scalar)/d(term_s): for `total.backward()` they are w_box, w_obj[s], w_cls.
+ * `ws` is a caller-provided workspace of yb_loss_workspace_bytes(...) bytes shared by both stages.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct yb_loss_desc {
+    int S;                          /* number of scales, 1..YB_MAX_SCALES */
+    int B;                          /* local batch */
+    long long B_global;             /* global batch (== B on one GPU): obj mean normaliser */
+    int A, nc;
+    int H[YB_MAX_SCALES], W[YB_MAX_SCALES];
+    float img_size;                 /* decode img_size, 640 in the reference's loss (:796) */
+    float eps;                      /* CIoU eps, 1e-7 (:634) */
+    float w_box, w_cls;             /* 0.05, 0.5 (:836) */
+    float w_obj[YB_MAX_SCALES];     /* 1.0 for yolo_loss; [4.0,1.0,0.4] multiscale (:865) */
+    float coef_box[YB_MAX_SCALES];  /* upstream coefficients for the gradient */
+    float coef_obj[YB_MAX_SCALES];
+    float coef_cls[YB_MAX_SCALES];
+    const float* pred[YB_MAX_SCALES];
+    const float* tgt[YB_MAX_SCALES];
+    const float* anchors[YB_MAX_SCALES];
+    float* grad[YB_MAX_SCALES];     /* nullable: forward only (torch.no_grad callers) */
+} yb_loss_desc;
+
+size_t yb_loss_workspace_bytes(const yb_loss_desc* d);
+int yb_loss_partials(const yb_loss_desc* d, double* partials /* S*4 */,
+                     void* ws, size_t ws_bytes, void* stream);
+int yb_loss_finalize(const yb_loss_desc* d, const double* partials /* S*4, reduced */,
+                     float* out4, float* per_scale /* S*3, nullable */,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* x[i] *= *factor for i < n, skipped entirely (no memory traffic) when *factor == 1.0f.
+ * Used by the autograd wrapper to apply the upstream gradient of `total` to the gradient the
+ * fused kernel already produced (loss.backward() passes exactly 1.0).  factor is a device pointer. */
+int yb_scale_inplace(float* x, long long n, const float* factor, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a-5  target assignment                                         train.py:108-131, 147-205
+ *   yb_anchor_iou: YOLODataset.compute_anchor_iou for n boxes x A anchors (fp32, +1e-16).
+ *   yb_build_targets: the label loop of YOLODataset.__getitem__ for a batch.
+ *     labels   (B, max_gt, 5) fp64 = raw label lines [class, xc, yc, w, h]
+ *     n_gt     (B) int32
+ *     letterbox(B, 5) fp64 = [orig_w, orig_h, scale, pad_top, pad_left]  (:136-137)
+ *     anchors  (S, A, 2) fp32
+ *     targets[s] (B, G_s, G_s, A, 5+nc) fp32, fully written (zero-filled then assigned)
+ *   Bit-exact with the reference: fp64 letterbox/cell math (:159-166,:184-189), fp32 shape IoU,
+ *   strict '>' across scales then first argmax (:177-180), first GT wins a slot (:193),
+ *   nc==1 writes class slot 5 irrespective of label id (:201-202).  Python's negative-index
+ *   wrap-around for cells in [-G, 0) is reproduced; rows the reference would reject
+ *   (IndexError) set bit 0 of *status (device int32, nullable).
+ * ---------------------------------------------------------------------------------------- */
+int yb_anchor_iou(const float* box_wh, const float* anchors, float* iou_out,
+                  int n, int A, void* stream);
+int yb_build_targets(const double* labels, const int* n_gt, const double* letterbox,
+                     const float* anchors, float* const targets_host[YB_MAX_SCALES],
+                     int B, int max_gt, int S, const int* G_host, int A, int nc, int img_size,
+                     int* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a-6  candidate filter + box build of predict()                  train.py:1152-1222, 1227-1229
+ *   For every image b and every row in P3->P4->P5, row-major (gy,gx,a) order:
+ *     keep rows with sigmoid(obj) > conf  (:1166-1167, objectness only)
+ *     class prob/id = max sigmoid(cls) (first max; nc==1: slot 5, id 0)  (:1184-1189)
+ *     xyxy in pixels, minus (pad_left,pad_top), divided by scale  (:1192-1213)
+ *     score = sigmoid(obj) * class prob  (:1216)
+ *   Output is per image, order preserving, with a fixed stride of `cap` candidates per image:
+ *     boxes (B,cap,4) fp32, scores (B,cap) fp32, classes (B,cap) int64, counts (B) int32.
+ *   letterbox (B,3) fp32 = [scale, pad_top, pad_left], NULL = identity.
+ *   cap must be >= total rows per image (sum_s H_s*W_s*A) unless the caller knows better;
+ *   candidates beyond cap are dropped and counts[b] saturates at cap.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct yb_heads_desc {
+    int S, B, A, nc;
+    int H[YB_MAX_SCALES], W[YB_MAX_SCALES];
+    float img_size;
+    const float* pred[YB_MAX_SCALES];
+    const float* anchors[YB_MAX_SCALES];
+} yb_heads_desc;
+
+size_t yb_filter_workspace_bytes(const yb_heads_desc* d);
+int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const float* letterbox,
+                      float* boxes, float* scores, int64_t* classes, int* counts, int cap,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a-7  torchvision.ops.batched_nms(boxes, scores, idxs, iou_threshold)       train.py:1232-1233
+ *      (torchvision 0.26.0, torchvision/ops/boxes.py:51-120 and its CUDA nms kernel)
+ *   Batched over B independent images with a fixed stride of `cap` candidates per image and
+ *   counts[b] valid entries (counts == NULL: every image has `cap`).
+ *   classes == NULL gives plain torchvision.ops.nms.
+ *   Arithmetic is torchvision's CUDA kernel bit for bit: fp32,
+ *     inter = max(0, min(ax2,bx2)-max(ax1,bx1)) * max(0, min(ay2,by2)-max(ay1,by1))
+ *     iou   = inter / ( fma(bx2-bx1, by2-by1, (ax2-ax1)*(ay2-ay1)) - inter ),  a = higher score
+ *     suppress when iou > (float)iou_threshold; stable descending score order (lower index wins
+ *     ties).
+ *   trick_max_numel reproduces batched_nms' size dispatch (boxes.py:80): an image with
+ *   4*counts[b] <= trick_max_numel uses the coordinate-offset trick (boxes + cls*(max+1), fp32,
+ *   boxes.py:98-101), larger ones the per-class loop (boxes.py:113-120).  Pass 100000 for CUDA
+ *   callers, 4000 for CPU callers, -1 to force per-class, LLONG_MAX to force the trick.
+ *   Output: keep (B,cap) int64 = kept candidate indices (0..counts[b]) in descending score order,
+ *   n_keep (B) int32.  Class ids must satisfy 0 <= id < 65536.
+ * ---------------------------------------------------------------------------------------- */
+size_t yb_nms_workspace_bytes(int B, int cap);      /* worst case: never overflows */
+size_t yb_nms_min_workspace_bytes(int B, int cap);  /* fixed part; anything above it holds mask rows.
+                                                       An image whose suppression-mask rows do not fit
+                                                       reports n_keep[b] = -1 (retry with more). */
+int yb_batched_nms(const float* boxes, const float* scores, const int64_t* classes,
+                   const int* counts, int B, int cap, double iou_threshold,
+                   long long trick_max_numel, int64_t* keep, int* n_keep,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* Counters for tests/bench: number of kernel launches this library has enqueued (process wide). */
+unsigned long long yb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO_B200_H */

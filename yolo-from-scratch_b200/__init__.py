@@ -1,0 +1,17 @@
+"""yolo_from_scratch_b200 — B200-native per-box detection hot path of KhaledSharif/yolo-from-scratch.
+
+decode -> (target assignment + CIoU/objectness/class loss, forward+backward) -> cross-scale global
+NMS, as hand-written sm_100a CUDA kernels in libyolo_b200.so (C-ABI: include/yolo_b200.h), with
+the reference's own Python function signatures on top (ops.py) and an installer that swaps them
+into the reference's `train` module (install.py).
+"""
+from . import _lib
+from .ops import (batched_nms, batched_nms_padded, build_targets, ciou_loss, compute_anchor_iou,
+                  decode_predictions, detect_batch, detections_to_lists, filter_candidates,
+                  loss_forward_backward, nms, yolo_loss, yolo_loss_multiscale)
+
+__all__ = [
+    "decode_predictions", "ciou_loss", "yolo_loss", "yolo_loss_multiscale", "compute_anchor_iou",
+    "build_targets", "filter_candidates", "nms", "batched_nms", "batched_nms_padded", "detect_batch",
+    "detections_to_lists", "loss_forward_backward",
+]

@@ -1,0 +1,123 @@
+// yb_decode.cu — K1 / K1b: decode_predictions forward and its vector-Jacobian product.
+// Reference: train.py:712-779.  Bound: HBM (read T + write T forward; read 2T + write T backward).
+//
+// Layout: the head tensor is one contiguous fp32 array of B*H*W*A rows of (5+nc) floats.
+// Both kernels walk it as flat float4 (128-bit) vectors — fully coalesced for any nc — and
+// recover (row, channel) with an exact multiply-shift division; only channels 0..3 of a row do
+// arithmetic, everything else is a straight copy.
+#include "yb_common.cuh"
+
+namespace yb {
+
+struct DecodeArgs {
+    const float* pred;
+    const float* anchors;   // (A,2) device
+    const float* grad_out;  // bwd only
+    float* out;             // fwd: decoded; bwd: grad_in
+    uint32_t n_vec;         // number of whole float4
+    uint32_t n_elem;        // total floats
+    uint32_t row;           // 5+nc
+    int A, W, H;
+    FastDiv d_row, d_A, d_W, d_H;
+    DecodeConsts k;
+};
+
+template <bool BWD>
+__device__ __forceinline__ float decode_elem(const DecodeArgs& a, uint32_t r, uint32_t c, float x, float g) {
+    // r = flat row index ((b*H + gy)*W + gx)*A + an ; c = channel in row
+    if (c >= 4) return BWD ? g : x;
+    uint32_t cell, an, gy_b, gx, gy, bi;
+    a.d_A.divmod(r, cell, an);
+    a.d_W.divmod(cell, gy_b, gx);
+    a.d_H.divmod(gy_b, bi, gy);
+    if (!BWD) {
+        if (c == 0) return decode_xy(x, (float)gx, a.k.inv_w);
+        if (c == 1) return decode_xy(x, (float)gy, a.k.inv_h);
+        float anc = __ldg(a.anchors + an * 2 + (c - 2));
+        return decode_wh(x, anc, a.k.inv_img);
+    } else {
+        // autograd order of train.py:758-759,773-774 (see DESIGN.md "decode backward")
+        float s = sigmoidf_ref(x);
+        float ds = (1.0f - s) * s;  // sigmoid_backward: grad * ((1 - y) * y)
+        if (c < 2) {
+            float inv = (c == 0) ? a.k.inv_w : a.k.inv_h;
+            return ((g * inv) * 2.0f) * ds;
+        }
+        float anc = __ldg(a.anchors + an * 2 + (c - 2));
+        float u = 2.0f * s;
+        float gp = g * (anc * a.k.inv_img);  // mul backward
+        float gu = gp * (2.0f * u);          // pow(u,2) backward
+        return (gu * 2.0f) * ds;             // (2*s) backward, then sigmoid backward
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const float4* __restrict__ in4 = reinterpret_cast<const float4*>(a.pred);
+    const float4* __restrict__ g4 = reinterpret_cast<const float4*>(a.grad_out);
+    float4* __restrict__ out4 = reinterpret_cast<float4*>(a.out);
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < a.n_vec; v += stride) {
+        float4 x = __ldcs(in4 + v);
+        float4 g = BWD ? __ldcs(g4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t r, c;
+        a.d_row.divmod(v * 4u, r, c);
+        float xs[4] = {x.x, x.y, x.z, x.w};
+        float gs[4] = {g.x, g.y, g.z, g.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[k] = decode_elem<BWD>(a, r, c, xs[k], gs[k]);
+            if (++c == a.row) { c = 0; ++r; }
+        }
+        __stcs(out4 + v, make_float4(o[0], o[1], o[2], o[3]));
+    }
+    // scalar tail (n_elem not a multiple of 4)
+    if (blockIdx.x == 0 && threadIdx.x < (a.n_elem & 3u)) {
+        uint32_t e = a.n_vec * 4u + threadIdx.x, r, c;
+        a.d_row.divmod(e, r, c);
+        a.out[e] = decode_elem<BWD>(a, r, c, a.pred[e], BWD ? a.grad_out[e] : 0.f);
+    }
+}
+
+static int decode_launch(bool bwd, const float* pred, const float* anchors, const float* grad_out,
+                         float* out, int B, int H, int W, int A, int nc, float img_size,
+                         void* stream) {
+    YB_CHECK_ARG(pred && anchors && out && (!bwd || grad_out), "decode: null pointer");
+    YB_CHECK_ARG(B >= 0 && H > 0 && W > 0 && A > 0 && A <= YB_MAX_ANCHORS && nc >= 0,
+                 "decode: bad shape B=%d H=%d W=%d A=%d nc=%d", B, H, W, A, nc);
+    YB_CHECK_ARG(aligned16(pred) && aligned16(out) && (!bwd || aligned16(grad_out)),
+                 "decode: tensors must be 16-byte aligned");
+    unsigned long long n = (unsigned long long)B * H * W * A * (5 + nc);
+    YB_CHECK_ARG(n < (1ull << 32), "decode: tensor too large (%llu elements)", n);
+    if (n == 0) return 0;
+    DecodeArgs a;
+    a.pred = pred; a.anchors = anchors; a.grad_out = grad_out; a.out = out;
+    a.n_elem = (uint32_t)n; a.n_vec = (uint32_t)(n / 4); a.row = 5 + nc;
+    a.A = A; a.W = W; a.H = H;
+    a.d_row = FastDiv(5 + nc); a.d_A = FastDiv(A); a.d_W = FastDiv(W); a.d_H = FastDiv(H);
+    a.k.inv_w = 1.0f / (float)W; a.k.inv_h = 1.0f / (float)H; a.k.inv_img = 1.0f / img_size;
+    const int threads = 256;
+    unsigned long long want = ((unsigned long long)a.n_vec + threads - 1) / threads;
+    // 8 resident CTAs/SM x 148 SMs, grid-stride beyond that (multiple of the SM count)
+    unsigned long long cap = (unsigned long long)sm_count() * 8 * 4;
+    int blocks = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bwd) decode_kernel<true><<<blocks, threads, 0, st>>>(a);
+    else     decode_kernel<false><<<blocks, threads, 0, st>>>(a);
+    YB_LAUNCH_CHECK(bwd ? "decode_bwd" : "decode_fwd");
+    return 0;
+}
+
+}  // namespace yb
+
+extern "C" int yb_decode_fwd(const float* pred, const float* anchors, float* out, int B, int H,
+                             int W, int A, int nc, float img_size, void* stream) {
+    return yb::decode_launch(false, pred, anchors, nullptr, out, B, H, W, A, nc, img_size, stream);
+}
+
+extern "C" int yb_decode_bwd(const float* pred, const float* anchors, const float* grad_out,
+                             float* grad_in, int B, int H, int W, int A, int nc, float img_size,
+                             void* stream) {
+    return yb::decode_launch(true, pred, anchors, grad_out, grad_in, B, H, W, A, nc, img_size, stream);
+}

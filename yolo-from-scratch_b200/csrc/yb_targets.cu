@@ -1,0 +1,172 @@
+// yb_targets.cu — K2: anchor-to-ground-truth target assignment.
+// Reference: YOLODataset.compute_anchor_iou train.py:108-131 and the label loop of
+// YOLODataset.__getitem__ train.py:147-205.  Integer/index work: results are bit-exact.
+//
+// Bound: HBM write of the dense zero-filled targets (T bytes per scale, cudaMemsetAsync);
+// the assignment itself touches <= max_gt rows per image.  One CTA per image; the reference's
+// sequential "first ground truth wins a slot" rule (:193) is resolved in parallel: ground truth
+// i writes iff no j < i maps to the same (scale, cell, anchor) slot.
+#include "yb_common.cuh"
+
+namespace yb {
+
+__device__ __forceinline__ float shape_iou(float w, float h, float aw, float ah) {
+    // train.py:119-130, all fp32
+    const float box_area = w * h;
+    const float anchor_area = aw * ah;
+    const float inter = fminf(w, aw) * fminf(h, ah);
+    const float uni = (box_area + anchor_area) - inter;
+    return inter / (uni + 1e-16f);
+}
+
+__global__ void anchor_iou_kernel(const float* __restrict__ box_wh, const float* __restrict__ anchors,
+                                  float* __restrict__ out, int n, int A) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * A) return;
+    int b = i / A, k = i - b * A;
+    out[i] = shape_iou(box_wh[b * 2], box_wh[b * 2 + 1], anchors[k * 2], anchors[k * 2 + 1]);
+}
+
+struct TargetArgs {
+    const double* labels;     // (B,max_gt,5)
+    const int* n_gt;          // (B)
+    const double* letterbox;  // (B,5) orig_w, orig_h, scale, pad_top, pad_left
+    const float* anchors;     // (S,A,2)
+    float* tgt[YB_MAX_SCALES];
+    int G[YB_MAX_SCALES];
+    int S, A, nc, max_gt, img;
+    int* status;
+};
+
+struct GtSlot {
+    uint32_t key;  // 0xffffffff = rejected
+    float x, y, w, h;
+    int cls;
+};
+
+// python: int(v) truncates toward zero; the index then wraps once if negative (list/tensor
+// indexing), and is an IndexError outside [-G, G).
+__device__ __forceinline__ bool py_cell(double v, int G, int& cell) {
+    if (!(v == v) || fabs(v) > 2.0e9) return false;
+    int g = (int)v;
+    if (g > G - 1) g = G - 1;
+    if (g < 0) g += G;
+    if (g < 0) return false;
+    cell = g;
+    return true;
+}
+
+__global__ void __launch_bounds__(128) build_targets_kernel(const TargetArgs a) {
+    extern __shared__ GtSlot s_gt[];
+    const int b = blockIdx.x;
+    int n = a.n_gt[b];
+    n = n < 0 ? 0 : (n > a.max_gt ? a.max_gt : n);
+    const double ow = a.letterbox[b * 5 + 0], oh = a.letterbox[b * 5 + 1];
+    const double sc = a.letterbox[b * 5 + 2], pt = a.letterbox[b * 5 + 3], pl = a.letterbox[b * 5 + 4];
+    const double img = (double)a.img;
+    bool bad = false;
+
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double* L = a.labels + ((size_t)b * a.max_gt + i) * 5;
+        // :159-162 — python double arithmetic, left to right, no fusion
+        const double xc = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(L[1], ow), sc), pl), img);
+        const double yc = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(L[2], oh), sc), pt), img);
+        const double wd = __ddiv_rn(__dmul_rn(__dmul_rn(L[3], ow), sc), img);
+        const double hd = __ddiv_rn(__dmul_rn(__dmul_rn(L[4], oh), sc), img);
+        // :165-167 — pixels, then torch.tensor(...) rounds to fp32
+        const float wpx = (float)__dmul_rn(wd, img), hpx = (float)__dmul_rn(hd, img);
+        // :170-180 — best anchor over all scales: strict '>' across scales, first argmax within
+        float best = -1.0f;
+        int bs = 0, ba = 0;
+        for (int s = 0; s < a.S; ++s) {
+            float m = -1.0f;
+            int ma = 0;
+            for (int k = 0; k < a.A; ++k) {
+                const float* an = a.anchors + (s * a.A + k) * 2;
+                const float iou = shape_iou(wpx, hpx, an[0], an[1]);
+                if (k == 0 || iou > m) { m = iou; ma = k; }
+            }
+            if (m > best) { best = m; bs = s; ba = ma; }
+        }
+        // :183-189
+        const int G = a.G[bs];
+        int gx = 0, gy = 0;
+        GtSlot g;
+        g.cls = (int)L[0];
+        const bool ok = py_cell(__dmul_rn(xc, (double)G), G, gx) && py_cell(__dmul_rn(yc, (double)G), G, gy) &&
+                        (a.nc <= 1 || (g.cls >= 0 && g.cls < a.nc));
+        if (ok) {
+            g.key = ((uint32_t)bs << 28) | ((uint32_t)ba << 24) | ((uint32_t)gy << 12) | (uint32_t)gx;
+        } else {
+            g.key = 0xffffffffu;
+            bad = true;
+        }
+        g.x = (float)xc; g.y = (float)yc; g.w = (float)wd; g.h = (float)hd;  // :195-197
+        s_gt[i] = g;
+    }
+    __syncthreads();
+    const int row = 5 + a.nc;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const GtSlot g = s_gt[i];
+        if (g.key == 0xffffffffu) continue;
+        bool first = true;
+        for (int j = 0; j < i; ++j)
+            if (s_gt[j].key == g.key) { first = false; break; }  // :193 slot already owned
+        if (!first) continue;
+        const int s = g.key >> 28, an = (g.key >> 24) & 15, gy = (g.key >> 12) & 4095, gx = g.key & 4095;
+        const int G = a.G[s];
+        float* t = a.tgt[s] + ((((size_t)b * G + gy) * G + gx) * a.A + an) * row;
+        t[0] = g.x; t[1] = g.y; t[2] = g.w; t[3] = g.h;
+        t[4] = 1.0f;                                   // :199
+        if (a.nc == 1) t[5] = 1.0f;                    // :201-202
+        else if (a.nc > 1) t[5 + g.cls] = 1.0f;        // :205
+    }
+    if (bad && a.status) atomicOr(a.status, 1);
+}
+
+}  // namespace yb
+
+extern "C" int yb_anchor_iou(const float* box_wh, const float* anchors, float* iou_out, int n, int A,
+                             void* stream) {
+    using namespace yb;
+    YB_CHECK_ARG(n >= 0 && A > 0, "anchor_iou: bad shape");
+    if (n == 0) return 0;
+    YB_CHECK_ARG(box_wh && anchors && iou_out, "anchor_iou: null pointer");
+    int tot = n * A;
+    anchor_iou_kernel<<<(tot + 127) / 128, 128, 0, (cudaStream_t)stream>>>(box_wh, anchors, iou_out, n, A);
+    YB_LAUNCH_CHECK("anchor_iou_kernel");
+    return 0;
+}
+
+extern "C" int yb_build_targets(const double* labels, const int* n_gt, const double* letterbox,
+                                const float* anchors, float* const targets_host[YB_MAX_SCALES],
+                                int B, int max_gt, int S, const int* G_host, int A, int nc,
+                                int img_size, int* status, void* stream) {
+    using namespace yb;
+    YB_CHECK_ARG(B >= 0 && max_gt >= 0 && S >= 1 && S <= YB_MAX_SCALES && A > 0 && A <= YB_MAX_ANCHORS &&
+                     nc >= 0 && img_size > 0 && G_host && targets_host,
+                 "build_targets: bad arguments");
+    if (B == 0) return 0;
+    YB_CHECK_ARG(n_gt && letterbox && anchors && (max_gt == 0 || labels), "build_targets: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    TargetArgs a;
+    a.labels = labels; a.n_gt = n_gt; a.letterbox = letterbox; a.anchors = anchors;
+    a.S = S; a.A = A; a.nc = nc; a.max_gt = max_gt; a.img = img_size; a.status = status;
+    for (int s = 0; s < S; ++s) {
+        YB_CHECK_ARG(G_host[s] > 0 && G_host[s] <= 4096 && targets_host[s], "build_targets: bad scale %d", s);
+        a.G[s] = G_host[s];
+        a.tgt[s] = targets_host[s];
+        size_t bytes = (size_t)B * G_host[s] * G_host[s] * A * (5 + nc) * sizeof(float);
+        YB_CUDA(cudaMemsetAsync(targets_host[s], 0, bytes, st));  // :141-145 torch.zeros
+        count_launch();
+    }
+    if (status) YB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+    if (max_gt == 0) return 0;
+    size_t smem = (size_t)max_gt * sizeof(GtSlot);
+    YB_CHECK_ARG(smem <= 200 * 1024, "build_targets: max_gt=%d too large", max_gt);
+    if (smem > 48 * 1024)
+        YB_CUDA(cudaFuncSetAttribute(build_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    build_targets_kernel<<<B, 128, smem, st>>>(a);
+    YB_LAUNCH_CHECK("build_targets_kernel");
+    return 0;
+}

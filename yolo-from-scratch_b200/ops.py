@@ -1,0 +1,516 @@
+"""Host-side mirror of the reference's per-box hot-path functions (reference `train.py`).
+
+Same names, argument meaning and return values as the reference so that callers and tests read
+the same; the arithmetic runs in libyolo_b200.so (hand-written sm_100a kernels, C-ABI in
+include/yolo_b200.h).  PyTorch is used only for device memory, streams and autograd plumbing.
+
+  decode_predictions      train.py:712-779
+  ciou_loss               train.py:634-710
+  yolo_loss               train.py:781-838
+  yolo_loss_multiscale    train.py:840-886
+  compute_anchor_iou      train.py:108-131
+  build_targets           train.py:147-205 (label loop of YOLODataset.__getitem__), batched
+  filter_candidates       train.py:1152-1229 (per-scale body of predict), batched
+  nms / batched_nms       torchvision.ops as called at train.py:1232-1233
+  detect_batch            filter_candidates + batched_nms + gather (predict :1152-1238 for a batch)
+
+CPU tensors are accepted (the reference's tests pass CPU tensors): they are staged to the GPU,
+computed there, and staged back.  That is staging, not a fallback: without CUDA every function
+raises.
+"""
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import HeadsDesc, LossDesc, MAX_ANCHORS, MAX_SCALES
+
+# reference constants
+BOX_WEIGHT = 0.05                 # train.py:836
+CLS_WEIGHT = 0.5                  # train.py:836
+MULTISCALE_OBJ_WEIGHTS = (4.0, 1.0, 0.4)  # train.py:865
+LOSS_DECODE_IMG_SIZE = 640.0      # train.py:796 — yolo_loss always decodes with the default
+CIOU_EPS = 1e-7                   # train.py:634
+TRICK_MAX_NUMEL_CUDA = 100_000    # torchvision/ops/boxes.py:80
+TRICK_MAX_NUMEL_CPU = 4_000
+
+
+# --------------------------------------------------------------------------------------------
+# plumbing
+# --------------------------------------------------------------------------------------------
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "yolo_from_scratch_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """fp32, contiguous, on `dev`, 16-byte aligned (differentiable)."""
+    if t.device != dev:
+        t = t.to(dev)
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+_anchor_cache = {}
+
+
+def _anchors_dev(anchors, dev: torch.device) -> torch.Tensor:
+    """(A,2) fp32 anchors on the device; small host-side cache so a CPU anchor tensor is not
+    re-uploaded on every call."""
+    if isinstance(anchors, torch.Tensor):
+        if anchors.device == dev and anchors.dtype == torch.float32 and anchors.is_contiguous():
+            return anchors.detach()
+        key = (anchors.data_ptr(), anchors._version, tuple(anchors.shape), str(anchors.dtype), dev.index)
+        hit = _anchor_cache.get(key)
+        if hit is not None and torch.equal(hit[0], anchors.detach().cpu() if anchors.device.type != "cpu" else anchors.detach()):
+            return hit[1]
+        host = anchors.detach().to("cpu", torch.float32).contiguous()
+        out = host.to(dev)
+        if len(_anchor_cache) > 64:
+            _anchor_cache.clear()
+        _anchor_cache[key] = (host.clone(), out)
+        return out
+    return torch.tensor(anchors, dtype=torch.float32, device=dev).reshape(-1, 2).contiguous()
+
+
+def _check_head(t: torch.Tensor, what: str):
+    if t.dim() != 5:
+        raise ValueError(f"{what} must be (B, H, W, A, 5+nc), got {tuple(t.shape)}")
+    if t.shape[3] > MAX_ANCHORS:
+        raise ValueError(f"{what}: at most {MAX_ANCHORS} anchors per scale")
+    if t.shape[4] < 5:
+        raise ValueError(f"{what}: last dimension must be 5+nc")
+
+
+# --------------------------------------------------------------------------------------------
+# a-1 decode_predictions
+# --------------------------------------------------------------------------------------------
+class _DecodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, anchors, img_size):
+        B, H, W, A, row = pred.shape
+        out = torch.empty_like(pred)
+        _lib.check(_lib.lib().yb_decode_fwd(pred.data_ptr(), anchors.data_ptr(), out.data_ptr(),
+                                            B, H, W, A, row - 5, float(img_size), _stream()), "yb_decode_fwd")
+        ctx.save_for_backward(pred, anchors)
+        ctx.img_size = float(img_size)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        pred, anchors = ctx.saved_tensors
+        B, H, W, A, row = pred.shape
+        grad_out = _f32c(grad_out, pred.device)
+        grad_in = torch.empty_like(pred)
+        _lib.check(_lib.lib().yb_decode_bwd(pred.data_ptr(), anchors.data_ptr(), grad_out.data_ptr(),
+                                            grad_in.data_ptr(), B, H, W, A, row - 5, ctx.img_size, _stream()),
+                   "yb_decode_bwd")
+        return grad_in, None, None
+
+
+def decode_predictions(raw_preds: torch.Tensor, anchors, img_size=640) -> torch.Tensor:
+    """train.py:712-779.  (B,H,W,A,5+nc) raw logits -> same shape with xywh decoded to
+    normalised coordinates; objectness/class logits unchanged.  Differentiable."""
+    _check_head(raw_preds, "raw_preds")
+    dev = _device()
+    orig_dev, orig_dtype = raw_preds.device, raw_preds.dtype
+    with torch.cuda.device(dev):
+        pred = _f32c(raw_preds, dev)
+        anc = _anchors_dev(anchors, dev)
+        if anc.shape[0] != pred.shape[3]:
+            raise ValueError("anchors must be (num_anchors, 2)")
+        out = _DecodeFn.apply(pred, anc, img_size)
+    if out.dtype != orig_dtype:
+        out = out.to(orig_dtype)
+    return out if orig_dev == dev else out.to(orig_dev)
+
+
+# --------------------------------------------------------------------------------------------
+# a-2 ciou_loss
+# --------------------------------------------------------------------------------------------
+class _CiouFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_boxes, target_boxes, eps):
+        N = pred_boxes.shape[0]
+        L = _lib.lib()
+        loss = torch.empty(1, dtype=torch.float32, device=pred_boxes.device)
+        need_p, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gp = torch.empty_like(pred_boxes) if need_p else None
+        gt = torch.empty_like(target_boxes) if need_t else None
+        scratch = torch.empty(16, dtype=torch.uint8, device=pred_boxes.device)
+        _lib.check(L.yb_ciou_fwd_bwd(pred_boxes.data_ptr(), target_boxes.data_ptr(), N, float(eps),
+                                     loss.data_ptr(), _ptr(gp), _ptr(gt), scratch.data_ptr(), 16, _stream()),
+                   "yb_ciou_fwd_bwd")
+        ctx.grads = (gp, gt)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        gp, gt = ctx.grads
+        return (None if gp is None else gp * g), (None if gt is None else gt * g), None
+
+
+def ciou_loss(pred_boxes: torch.Tensor, target_boxes: torch.Tensor, eps=CIOU_EPS) -> torch.Tensor:
+    """train.py:634-710.  mean(1 - CIoU) over N (x,y,w,h) pairs."""
+    if pred_boxes.dim() != 2 or pred_boxes.shape[1] != 4 or pred_boxes.shape != target_boxes.shape:
+        raise ValueError("ciou_loss expects two (N,4) tensors")
+    dev = _device()
+    orig_dev = pred_boxes.device
+    with torch.cuda.device(dev):
+        p = _f32c(pred_boxes, dev)
+        t = _f32c(target_boxes, dev)
+        out = _CiouFn.apply(p, t, eps)
+    return out if orig_dev == dev else out.to(orig_dev)
+
+
+# --------------------------------------------------------------------------------------------
+# a-3 / a-4 fused loss
+# --------------------------------------------------------------------------------------------
+def _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=None, img_size=LOSS_DECODE_IMG_SIZE):
+    S = len(preds)
+    d = LossDesc()
+    d.S = S
+    d.B = preds[0].shape[0]
+    d.B_global = d.B if B_global is None else int(B_global)
+    d.A = preds[0].shape[3]
+    d.nc = nc
+    d.img_size = img_size
+    d.eps = CIOU_EPS
+    d.w_box, d.w_cls = BOX_WEIGHT, CLS_WEIGHT
+    for s in range(S):
+        d.H[s], d.W[s] = preds[s].shape[1], preds[s].shape[2]
+        d.w_obj[s] = obj_weights[s]
+        d.coef_box[s], d.coef_obj[s], d.coef_cls[s] = coef[s]
+        d.pred[s] = preds[s].data_ptr()
+        d.tgt[s] = tgts[s].data_ptr()
+        d.anchors[s] = ancs[s].data_ptr()
+        d.grad[s] = _ptr(grads[s])
+    return d
+
+
+def loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want_grad, coef=None, group=None):
+    """Run the fused kernels on device tensors.  Returns (out4, per_scale(S,3), grads list).
+
+    `group`: optional torch.distributed process group; the batch is then a shard of a global
+    batch and the S*4 partial sums are all-reduced once between the two stages.
+    """
+    L = _lib.lib()
+    S = len(preds)
+    dev = preds[0].device
+    if coef is None:
+        coef = [(BOX_WEIGHT, obj_weights[s], CLS_WEIGHT) for s in range(S)]
+    grads = [torch.empty_like(p) if w else None for p, w in zip(preds, want_grad)]
+    world = 1
+    if group is not None:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+    d = _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=preds[0].shape[0] * world)
+    ws_bytes = L.yb_loss_workspace_bytes(ctypes.byref(d))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    partials = torch.empty(S * 4, dtype=torch.float64, device=dev)
+    out4 = torch.empty(4, dtype=torch.float32, device=dev)
+    per_scale = torch.empty(S, 3, dtype=torch.float32, device=dev)
+    st = _stream()
+    _lib.check(L.yb_loss_partials(ctypes.byref(d), partials.data_ptr(), ws.data_ptr(), ws_bytes, st), "yb_loss_partials")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+    _lib.check(L.yb_loss_finalize(ctypes.byref(d), partials.data_ptr(), out4.data_ptr(), per_scale.data_ptr(),
+                                  ws.data_ptr(), ws_bytes, st), "yb_loss_finalize")
+    return out4, per_scale, grads
+
+
+class _YoloLossFn(torch.autograd.Function):
+    """(total, bbox, obj, cls) = f(preds...) with the gradient of `total` produced in the same
+    pass.  Gradients that arrive on bbox/obj/cls as well are honoured by re-running the kernels
+    with the combined coefficients (rare: the reference only calls total.backward())."""
+
+    @staticmethod
+    def forward(ctx, nc, obj_weights, group, S, *tensors):
+        preds, tgts, ancs = tensors[:S], tensors[S:2 * S], tensors[2 * S:3 * S]
+        want = [ctx.needs_input_grad[4 + s] for s in range(S)]
+        out4, per_scale, grads = loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want, group=group)
+        ctx.set_materialize_grads(False)
+        ctx.cfg = (nc, obj_weights, group, S, want)
+        ctx.fused_grads = grads
+        ctx.save_for_backward(*tensors)
+        return out4[0], out4[1], out4[2], out4[3]
+
+    @staticmethod
+    def backward(ctx, g_total, g_bbox, g_obj, g_cls):
+        nc, obj_weights, group, S, want = ctx.cfg
+        none = (None,) * 4
+        if not any(want):
+            return none + (None,) * (3 * S)
+        if g_bbox is None and g_obj is None and g_cls is None:
+            grads = ctx.fused_grads
+            if g_total is None:
+                grads = [None if g is None else torch.zeros_like(g) for g in grads]
+            else:
+                L = _lib.lib()
+                f = g_total.detach().to(torch.float32).reshape(1).contiguous()
+                for g in grads:
+                    if g is not None:
+                        _lib.check(L.yb_scale_inplace(g.data_ptr(), g.numel(), f.data_ptr(), _stream()),
+                                   "yb_scale_inplace")
+        else:
+            tensors = ctx.saved_tensors
+            preds, tgts, ancs = tensors[:S], tensors[S:2 * S], tensors[2 * S:3 * S]
+            z = lambda g: 0.0 if g is None else float(g)
+            gt_, gb_, go_, gc_ = z(g_total), z(g_bbox), z(g_obj), z(g_cls)
+            coef = [(BOX_WEIGHT * gt_ + gb_, obj_weights[s] * gt_ + go_, CLS_WEIGHT * gt_ + gc_) for s in range(S)]
+            _, _, grads = loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want, coef=coef, group=group)
+        ctx.fused_grads = None
+        return none + tuple(grads) + (None,) * (2 * S)
+
+
+def _loss_common(predictions, targets, anchors_list, num_classes, obj_weights, group=None):
+    S = len(predictions)
+    if not 1 <= S <= MAX_SCALES:
+        raise ValueError(f"1..{MAX_SCALES} scales supported, got {S}")
+    dev = _device()
+    orig_dev = predictions[0].device
+    with torch.cuda.device(dev):
+        preds, tgts, ancs = [], [], []
+        for s in range(S):
+            _check_head(predictions[s], f"predictions[{s}]")
+            if predictions[s].shape != targets[s].shape:
+                raise ValueError(f"scale {s}: predictions {tuple(predictions[s].shape)} vs targets {tuple(targets[s].shape)}")
+            if predictions[s].shape[4] != 5 + num_classes:
+                raise ValueError(f"scale {s}: last dim {predictions[s].shape[4]} != 5+num_classes")
+            preds.append(_f32c(predictions[s], dev))
+            tgts.append(_f32c(targets[s].detach(), dev))
+            ancs.append(_anchors_dev(anchors_list[s], dev))
+        outs = _YoloLossFn.apply(int(num_classes), tuple(float(w) for w in obj_weights), group, S, *preds, *tgts, *ancs)
+    if orig_dev != dev:
+        outs = tuple(o.to(orig_dev) for o in outs)
+    return outs
+
+
+def yolo_loss(predictions, targets, anchors, num_classes=1):
+    """train.py:781-838.  Returns (total, bbox, obj, cls) for one scale."""
+    return _loss_common([predictions], [targets], [anchors], num_classes, (1.0,))
+
+
+def yolo_loss_multiscale(predictions, targets, anchors_list, num_classes=1):
+    """train.py:840-886.  Returns (total, sum bbox, sum obj (unweighted), sum cls)."""
+    S = min(len(predictions), len(targets), len(anchors_list), len(MULTISCALE_OBJ_WEIGHTS))  # zip() semantics (:873)
+    return _loss_common(list(predictions[:S]), list(targets[:S]), list(anchors_list[:S]), num_classes,
+                        MULTISCALE_OBJ_WEIGHTS[:S])
+
+
+# --------------------------------------------------------------------------------------------
+# a-5 target assignment
+# --------------------------------------------------------------------------------------------
+def compute_anchor_iou(box_wh, anchors) -> torch.Tensor:
+    """train.py:108-131.  box_wh (2,) or (n,2) pixels, anchors (A,2) -> (A,) or (n,A) IoU."""
+    dev = _device()
+    box_wh = torch.as_tensor(box_wh)
+    orig_dev = box_wh.device
+    single = box_wh.dim() == 1
+    with torch.cuda.device(dev):
+        b = _f32c(box_wh.reshape(-1, 2), dev)
+        a = _anchors_dev(anchors, dev)
+        out = torch.empty(b.shape[0], a.shape[0], dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().yb_anchor_iou(b.data_ptr(), a.data_ptr(), out.data_ptr(), b.shape[0], a.shape[0], _stream()),
+                   "yb_anchor_iou")
+    out = out[0] if single else out
+    return out if orig_dev == dev else out.to(orig_dev)
+
+
+def build_targets(labels: Sequence, anchors_list, grid_sizes: Sequence[int], num_classes: int, img_size: int,
+                  letterbox: Optional[Sequence] = None, check: bool = True) -> List[torch.Tensor]:
+    """Label loop of YOLODataset.__getitem__ (train.py:147-205) for a batch of images.
+
+    labels: per image an (n_i, 5) array-like of raw label lines [class, xc, yc, w, h] (fp64)
+    letterbox: per image (orig_w, orig_h, scale, pad_top, pad_left) as returned by the
+               reference's letterbox_resize (:136-137); None = an img_size x img_size original.
+    Returns dense targets [ (B,G,G,A,5+nc) fp32 on the GPU for each scale ].
+    """
+    dev = _device()
+    B = len(labels)
+    S = len(grid_sizes)
+    with torch.cuda.device(dev):
+        anc = torch.stack([_anchors_dev(a, dev) for a in anchors_list]).contiguous()  # (S,A,2)
+        A = anc.shape[1]
+        rows = [torch.as_tensor(l, dtype=torch.float64).reshape(-1, 5) for l in labels]
+        max_gt = max([r.shape[0] for r in rows], default=0)
+        lab = torch.zeros(B, max(max_gt, 1), 5, dtype=torch.float64)
+        n_gt = torch.zeros(B, dtype=torch.int32)
+        for i, r in enumerate(rows):
+            lab[i, :r.shape[0]] = r
+            n_gt[i] = r.shape[0]
+        if letterbox is None:
+            lb = torch.tensor([[img_size, img_size, 1.0, 0.0, 0.0]] * B, dtype=torch.float64).reshape(B, 5)
+        else:
+            lb = torch.as_tensor(letterbox, dtype=torch.float64).reshape(B, 5)
+        lab_d, n_d, lb_d = lab.to(dev), n_gt.to(dev), lb.to(dev)
+        row = 5 + num_classes
+        targets = [torch.empty(B, g, g, A, row, dtype=torch.float32, device=dev) for g in grid_sizes]
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        tptr = (ctypes.c_void_p * MAX_SCALES)(*[t.data_ptr() for t in targets])
+        G = (ctypes.c_int * S)(*[int(g) for g in grid_sizes])
+        _lib.check(_lib.lib().yb_build_targets(lab_d.data_ptr(), n_d.data_ptr(), lb_d.data_ptr(), anc.data_ptr(), tptr,
+                                               B, max_gt, S, G, A, int(num_classes), int(img_size),
+                                               status.data_ptr(), _stream()), "yb_build_targets")
+        if check and int(status.item()) != 0:
+            raise IndexError("build_targets: a label maps outside the grid or the class range "
+                             "(the reference raises IndexError on the same input, train.py:193-205)")
+    return targets
+
+
+# --------------------------------------------------------------------------------------------
+# a-6 candidate filter, a-7 NMS
+# --------------------------------------------------------------------------------------------
+def _heads_desc(preds, ancs, img_size, nc):
+    d = HeadsDesc()
+    d.S, d.B, d.A, d.nc = len(preds), preds[0].shape[0], preds[0].shape[3], nc
+    d.img_size = float(img_size)
+    for s, p in enumerate(preds):
+        d.H[s], d.W[s] = p.shape[1], p.shape[2]
+        d.pred[s] = p.data_ptr()
+        d.anchors[s] = ancs[s].data_ptr()
+    return d
+
+
+def filter_candidates(predictions, anchors_list, img_size, num_classes=1, conf_threshold=0.5, letterbox=None):
+    """Per-scale body of predict() (train.py:1152-1229) for a batch: decode, sigmoid, objectness
+    filter, class max, pixel xyxy with letterbox reverse, score; P3->P4->P5 order preserved.
+
+    letterbox: (B,3) [scale, pad_top, pad_left] or None.
+    Returns (boxes (B,cap,4), scores (B,cap), classes (B,cap) int64, counts (B,) int32) on the GPU,
+    cap = rows per image.
+    """
+    dev = _device()
+    S = len(predictions)
+    with torch.cuda.device(dev):
+        preds = [_f32c(p.detach(), dev) for p in predictions]
+        for s, p in enumerate(preds):
+            _check_head(p, f"predictions[{s}]")
+        ancs = [_anchors_dev(a, dev) for a in anchors_list[:S]]
+        B = preds[0].shape[0]
+        cap = sum(p.shape[1] * p.shape[2] * p.shape[3] for p in preds)
+        d = _heads_desc(preds, ancs, img_size, int(num_classes))
+        L = _lib.lib()
+        ws_bytes = L.yb_filter_workspace_bytes(ctypes.byref(d))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        boxes = torch.empty(B, cap, 4, dtype=torch.float32, device=dev)
+        scores = torch.empty(B, cap, dtype=torch.float32, device=dev)
+        classes = torch.empty(B, cap, dtype=torch.int64, device=dev)
+        counts = torch.zeros(B, dtype=torch.int32, device=dev)
+        lb = None
+        if letterbox is not None:
+            lb = torch.as_tensor(letterbox, dtype=torch.float32).reshape(B, 3).to(dev).contiguous()
+        _lib.check(L.yb_filter_compact(ctypes.byref(d), float(conf_threshold), _ptr(lb), boxes.data_ptr(),
+                                       scores.data_ptr(), classes.data_ptr(), counts.data_ptr(), cap,
+                                       ws.data_ptr(), ws.numel(), _stream()), "yb_filter_compact")
+    return boxes, scores, classes, counts
+
+
+_nms_ws_cache = {}
+
+
+def _nms_workspace(B, cap, dev, full):
+    L = _lib.lib()
+    need = L.yb_nms_workspace_bytes(B, cap) if full else min(
+        L.yb_nms_workspace_bytes(B, cap), L.yb_nms_min_workspace_bytes(B, cap) + (256 << 20))
+    return torch.empty(need, dtype=torch.uint8, device=dev)
+
+
+def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel=TRICK_MAX_NUMEL_CUDA):
+    """NMS for B images at once.  boxes (B,cap,4), scores (B,cap), classes (B,cap) int64 or None,
+    counts (B,) int32 or None.  Returns (keep (B,cap) int64, n_keep (B,) int32) on the GPU."""
+    dev = boxes.device
+    B, cap = boxes.shape[0], boxes.shape[1]
+    L = _lib.lib()
+    keep = torch.empty(B, cap, dtype=torch.int64, device=dev)
+    n_keep = torch.zeros(B, dtype=torch.int32, device=dev)
+    if B == 0 or cap == 0:
+        return keep, n_keep
+    ws = _nms_workspace(B, cap, dev, full=True)
+    _lib.check(L.yb_batched_nms(boxes.data_ptr(), scores.data_ptr(), _ptr(classes), _ptr(counts), B, cap,
+                                float(iou_threshold), int(trick_max_numel), keep.data_ptr(), n_keep.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream()), "yb_batched_nms")
+    return keep, n_keep
+
+
+def _nms_single(boxes, scores, idxs, iou_threshold):
+    if boxes.dim() != 2 or boxes.shape[1] != 4:
+        raise ValueError("boxes must be (N,4)")
+    dev = _device()
+    orig_dev = boxes.device
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=orig_dev)
+    with torch.cuda.device(dev):
+        b = _f32c(boxes.detach(), dev).unsqueeze(0)
+        s = _f32c(scores.detach(), dev).unsqueeze(0)
+        c = None
+        if idxs is not None:
+            c = idxs.detach().to(dev, torch.int64).contiguous().unsqueeze(0)
+        # torchvision picks its algorithm from the caller's device (boxes.py:80)
+        trick = TRICK_MAX_NUMEL_CPU if orig_dev.type == "cpu" else TRICK_MAX_NUMEL_CUDA
+        keep, n_keep = batched_nms_padded(b, s, c, None, iou_threshold, trick)
+        k = int(n_keep[0].item())
+        if k < 0:
+            raise ValueError("batched_nms: class ids must be in [0, 65536)")
+        out = keep[0, :k].clone()
+    return out if orig_dev == dev else out.to(orig_dev)
+
+
+def batched_nms(boxes, scores, idxs, iou_threshold):
+    """Drop-in for torchvision.ops.batched_nms (train.py:1232-1233): int64 indices of the kept
+    boxes in descending score order."""
+    return _nms_single(boxes, scores, idxs, iou_threshold)
+
+
+def nms(boxes, scores, iou_threshold):
+    """Drop-in for torchvision.ops.nms."""
+    return _nms_single(boxes, scores, None, iou_threshold)
+
+
+def detect_batch(predictions, anchors_list, img_size, num_classes=1, conf_threshold=0.5, iou_threshold=0.4,
+                 letterbox=None, trick_max_numel=TRICK_MAX_NUMEL_CUDA):
+    """predict() lines 1152-1238 for a whole batch on the GPU: decode + filter + global NMS.
+
+    Returns a dict of device tensors: boxes (B,cap,4), scores, classes, counts (candidates per
+    image), keep (B,cap) indices into the candidates in descending score order, n_keep (B,).
+    Nothing is synchronised; use `detections_to_lists` for the reference's list-of-tuples form.
+    """
+    boxes, scores, classes, counts = filter_candidates(predictions, anchors_list, img_size, num_classes,
+                                                       conf_threshold, letterbox)
+    with torch.cuda.device(boxes.device):
+        keep, n_keep = batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel)
+    return {"boxes": boxes, "scores": scores, "classes": classes, "counts": counts, "keep": keep, "n_keep": n_keep}
+
+
+def detections_to_lists(det):
+    """[(x1, y1, x2, y2, conf, class_id), ...] per image (train.py:1242-1246), one D2H copy."""
+    n_keep = det["n_keep"].cpu()
+    if (n_keep < 0).any():
+        raise RuntimeError("NMS workspace overflow or class id out of range")
+    out = []
+    for b in range(n_keep.numel()):
+        k = int(n_keep[b])
+        idx = det["keep"][b, :k]
+        bx = det["boxes"][b].index_select(0, idx).cpu()
+        sc = det["scores"][b].index_select(0, idx).cpu()
+        cl = det["classes"][b].index_select(0, idx).cpu()
+        out.append([(float(bx[i, 0]), float(bx[i, 1]), float(bx[i, 2]), float(bx[i, 3]), float(sc[i]), int(cl[i]))
+                    for i in range(k)])
+    return out
