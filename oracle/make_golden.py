@@ -257,8 +257,10 @@ def golden_model_heads():
         path = os.path.join(tmp, "x.png")
         Image.fromarray(np.zeros((640, 640, 3), dtype=np.uint8)).save(path)
         fake = FakeModel(heads, 640, model.anchors)
-        obj = torch.cat([torch.sigmoid(h[..., 4]).reshape(-1) for h in heads])
-        confs = [float(torch.quantile(obj, q)) for q in (0.90, 0.99)]
+        # the bias init puts every sigmoid(obj) within 50 ulp of 0.01 (105 distinct values), so a
+        # threshold inside that cluster is decided by the last bit of the sigmoid implementation;
+        # 0.009 passes every row: a dense, heavily tied NMS input
+        confs = [0.009]
         out["confs"] = np.array(confs, dtype=np.float64)
         for k, conf in enumerate(confs):
             dets = ref.predict(fake, path, torch.device("cpu"), num_classes=1, conf_threshold=conf, iou_threshold=0.4)

@@ -627,7 +627,7 @@ extern "C" size_t yb_nms_workspace_bytes(int B, int cap) {
 
 extern "C" size_t yb_nms_min_workspace_bytes(int B, int cap) {
     if (B <= 0 || cap <= 0) return 256;
-    return yb::nms_layout(B, cap).total + 8192;
+    return yb::nms_layout(B, cap).total + (size_t)B * 32;
 }
 
 extern "C" int yb_batched_nms(const float* boxes, const float* scores, const int64_t* classes,
@@ -648,7 +648,7 @@ extern "C" int yb_batched_nms(const float* boxes, const float* scores, const int
     YB_CHECK_ARG(B <= 65535, "nms: B too large");
     YB_CHECK_ARG(cap <= 400000, "nms: cap too large");
     NmsLayout L = nms_layout(B, cap);
-    YB_CHECK_ARG(ws_bytes > L.total + 4096, "nms: workspace too small (%zu <= %zu)", ws_bytes, L.total + 4096);
+    YB_CHECK_ARG(ws_bytes >= L.total + (size_t)B * 32, "nms: workspace too small (%zu < %zu)", ws_bytes, L.total + (size_t)B * 32);
     char* w = reinterpret_cast<char*>(ws);
     NmsArgs a;
     a.boxes = reinterpret_cast<const float4*>(boxes); a.scores = scores; a.classes = classes; a.counts = counts;
