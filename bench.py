@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py — decode+global-NMS images/s and CIoU-loss fwd+bwd ms @640^2 bs64 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the per-box hot path over one batch of synthetic heads/labels:
+fused multi-scale loss forward+backward, then decode + confidence filter + global NMS.
+Workload = BASELINE.json configs[1]: nc=1, 640x640, 64 images per GPU, <=50 GT boxes per image,
+randn heads (seed 1234+scale), predict()'s default thresholds (conf 0.5, IoU 0.4; train.py:1114).
+N GPUs = 64 images on each (weak scaling, sharded by image); the loss partial sums are all-reduced
+once per step over NCCL, NMS needs no collective.
+
+`value` is timed with the inputs resident in HBM; `e2e` goes through the public Python API with
+pinned HOST buffers (H2D of heads+targets and D2H of losses + detections inside the timed region).
+`--impl reference` times the oracle port of the reference's CPU implementation (torch CPU ops +
+torchvision's CPU nms, the code path train.py runs on a host without CUDA) on a bounded sample.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+IMG, NC, B_PER_GPU, MAX_GT = 640, 1, 64, 50
+CONF, IOU = 0.5, 0.4
+N_SETS = 4
+METRIC = "decode+global-NMS + CIoU-loss fwd+bwd throughput @640^2 bs64 nc1"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nc", type=int, default=NC)
+    ap.add_argument("--img", type=int, default=IMG)
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU")
+    ap.add_argument("--conf", type=float, default=CONF)
+    ap.add_argument("--iou", type=float, default=IOU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------
+def make_labels(rng, B, nc):
+    labels = []
+    for _ in range(B):
+        n = int(rng.integers(0, MAX_GT + 1))
+        lab = np.zeros((n, 5), dtype=np.float64)
+        lab[:, 0] = rng.integers(0, nc, size=n)
+        lab[:, 1:3] = rng.uniform(0.05, 0.95, size=(n, 2))
+        lab[:, 3:5] = np.exp(rng.uniform(np.log(0.01), np.log(0.6), size=(n, 2)))
+        labels.append(lab)
+    return labels
+
+
+def make_heads(B, img, nc, seed):
+    grids = [img // 8, img // 16, img // 32]
+    heads = []
+    for s, G in enumerate(grids):
+        g = torch.Generator().manual_seed(seed + s)
+        heads.append(torch.randn(B, G, G, 3, 5 + nc, generator=g))
+    return heads
+
+
+def tensor_bytes(ts):
+    return int(sum(t.numel() * t.element_size() for t in ts))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvml)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle port of the reference's CPU path
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(heads, tgts, anchors, nc, img, conf, iou, pool, use_tv):
+    """loss fwd+bwd (torch CPU, all threads) + per-image decode/filter/NMS (train.py:1152-1238)."""
+    from oracle import ref_path as R
+    preds = [h.clone().requires_grad_(True) for h in heads]
+    total = R.multiscale_loss(preds, tgts, anchors, nc)[0]
+    total.backward()
+    B = heads[0].shape[0]
+
+    def one(b):
+        bx, sc, cl = R.candidates([h[b:b + 1] for h in heads], anchors, img, nc, conf)
+        if bx.shape[0] == 0:
+            return 0
+        if use_tv:
+            import torchvision
+            return int(torchvision.ops.batched_nms(bx, sc, cl, iou).numel())
+        return len(R.batched_nms_indices(bx.numpy(), sc.numpy(), cl.numpy(), iou, "cpu", "cpu"))
+    kept = list(pool.map(one, range(B)))
+    return float(total), kept
+
+
+def run_cpu_reference(args, sample_images, steps, warmup):
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import ref_path as R
+    try:
+        import torchvision  # noqa: F401
+        use_tv = True
+    except Exception:
+        use_tv = False
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    anchors = R.default_anchors()
+    heads = [h[:sample_images].contiguous() for h in make_heads(args.batch, args.img, args.nc, 1234)]
+    labels = make_labels(np.random.default_rng(4321), args.batch, args.nc)[:sample_images]
+    grids = [args.img // 8, args.img // 16, args.img // 32]
+    tg = [R.assign_targets(l, anchors, grids, args.nc, args.img) for l in labels]
+    tgts = [torch.from_numpy(np.stack([t[s] for t in tg])) for s in range(3)]
+    pool = ThreadPoolExecutor(max_workers=min(cores, sample_images))
+    for _ in range(warmup):
+        cpu_reference_step(heads, tgts, anchors, args.nc, args.img, args.conf, args.iou, pool, use_tv)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(heads, tgts, anchors, args.nc, args.img, args.conf, args.iou, pool, use_tv)
+    dt = (time.perf_counter() - t0) / steps
+    pool.shutdown()
+    sample = (f"{sample_images} of {args.batch} images per step (same seeds), loss fwd+bwd on torch CPU + per-image "
+              f"decode/filter/{'torchvision CPU batched_nms' if use_tv else 'nms_ref.c'}; images spread over {min(cores, sample_images)} threads")
+    return sample_images / dt, dt * 1e3, cores, sample
+
+
+def reference_main(args, rank):
+    if rank != 0:
+        return
+    sample_images = max(1, min(args.batch, 8))
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    v, ms, cores, sample = run_cpu_reference(args, sample_images, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"BASELINE configs[1]: nc={args.nc} heads at {args.img}x{args.img}, {args.batch} images/GPU, "
+                    f"<= {MAX_GT} GT boxes/image, randn heads, conf {args.conf}, iou {args.iou}",
+        "global_batch": args.batch * world, "images_per_gpu": args.batch, "img_size": args.img, "nc": args.nc,
+        "conf_thres": args.conf, "iou_thres": args.iou, "parallelism": f"image-sharded x{world}",
+        "l2": f"inputs rotate over {N_SETS} sets per rank (working set > 126 MB L2)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def b200_main(args, rank, local_rank, world):
+    import yolo_from_scratch_b200 as yb
+    from yolo_from_scratch_b200 import ops
+    lib = yb._lib.lib()  # raises if the CUDA extension is missing: no fallback
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl b200) needs a GPU; the CUDA path has no fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    B, img, nc = args.batch, args.img, args.nc
+    grids = [img // 8, img // 16, img // 32]
+    from oracle.ref_path import default_anchors  # constants only (train.py:372-374)
+    anchors = [a.to(dev) for a in default_anchors()]
+    weights = ops.MULTISCALE_OBJ_WEIGHTS
+
+    # N_SETS input sets per rank, on the device and mirrored in pinned host memory
+    dev_sets, host_sets = [], []
+    for k in range(N_SETS):
+        seed = 1234 + 1000 * k + 100000 * rank
+        heads = make_heads(B, img, nc, seed)
+        labels = make_labels(np.random.default_rng(4321 + k + 1000 * rank), B, nc)
+        tg = ops.build_targets(labels, anchors, grids, nc, img)
+        d_heads = [h.to(dev) for h in heads]
+        dev_sets.append((d_heads, tg))
+        host_sets.append(([h.pin_memory() for h in heads], [t.cpu().pin_memory() for t in tg]))
+    torch.cuda.synchronize()
+    T_bytes = tensor_bytes(dev_sets[0][0])
+    rows = sum(B * G * G * 3 for G in grids)
+    row_bytes = (5 + nc) * 4
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident step ------------------------------------------------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+
+    def step(i, conf=None, record=None):
+        heads, tg = dev_sets[i % N_SETS]
+        if record:
+            record[0].record()
+        out4, per_scale, grads = ops.loss_forward_backward(heads, tg, anchors, nc, weights, [True] * 3, group=group)
+        if record:
+            record[1].record()
+        det = ops.detect_batch(heads, anchors, img, nc, args.conf if conf is None else conf, args.iou)
+        if record:
+            record[2].record()
+        return out4, det
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    # candidate statistics per input set (outside the timed region)
+    pair_counts, cand_counts, keep_counts = [], [], []
+    for k in range(N_SETS):
+        _, det = step(k)
+        m = det["counts"].cpu().double()
+        cand_counts.append(float(m.sum()))
+        pair_counts.append(float((m * (m - 1) / 2).sum()))
+        keep_counts.append(float(det["n_keep"].cpu().double().sum()))
+        assert int(det["n_keep"].min()) >= 0
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.yb_timing_enable(1)
+    launches0 = lib.yb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i, record=ev[i])
+    e1.record()
+    barrier()
+    launches = lib.yb_launch_count() - launches0
+    lib.yb_timing_enable(0)
+    sampler.stop_flag = True
+    sampler.join()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = total_ms / args.steps
+    loss_ms = float(np.mean([r[0].elapsed_time(r[1]) for r in ev]))
+    det_ms = float(np.mean([r[1].elapsed_time(r[2]) for r in ev]))
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.yb_timing_collect(buf, len(buf))
+    kernels = {}
+    for ln in buf.value.decode().strip().splitlines():
+        name, cnt, tot = ln.split()
+        kernels[name] = {"launches_per_step": int(cnt) / args.steps, "avg_ms": float(tot) / int(cnt),
+                         "ms_per_step": float(tot) / args.steps}
+    ksum = sum(k["ms_per_step"] for k in kernels.values())
+    for k in kernels.values():
+        k["share"] = k["ms_per_step"] / ksum if ksum else 0.0
+
+    # ---- e2e through the public API with host buffers ---------------------------------------------
+    loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    off_host = torch.empty(B + 1, dtype=torch.int32).pin_memory()
+    det_host = torch.empty(B * sum(G * G * 3 for G in grids), 6, dtype=torch.float32).pin_memory()
+    h2d = tensor_bytes(host_sets[0][0]) + tensor_bytes(host_sets[0][1])
+    d2h_acc = []
+
+    def e2e_step(i):
+        h_heads, h_tg = host_sets[i % N_SETS]
+        preds = [h.to(dev, non_blocking=True).requires_grad_(True) for h in h_heads]
+        tgts = [t.to(dev, non_blocking=True) for t in h_tg]
+        if group is None:
+            total, bbox, obj, cls = yb.yolo_loss_multiscale(preds, tgts, anchors, nc)
+        else:
+            total, bbox, obj, cls = ops._loss_common(preds, tgts, anchors, nc, weights, group=group)
+        total.backward()
+        loss_host.copy_(torch.stack([total.detach(), bbox.detach(), obj.detach(), cls.detach()]), non_blocking=True)
+        det = yb.detect_batch([p.detach() for p in preds], anchors, img, nc, args.conf, args.iou)
+        rows_d, offsets = yb.pack_detections(det)
+        off_host.copy_(offsets, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n = int(off_host[-1])
+        det_host[:n].copy_(rows_d[:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        d2h_acc.append(16 + off_host.numel() * 4 + n * 24)
+        return preds
+
+    for i in range(max(3, args.warmup)):
+        e2e_step(i)
+    d2h_acc.clear()
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    g1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)) / args.steps
+    e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(np.mean(d2h_acc)),
+           "api": "yolo_loss_multiscale(...).backward() + detect_batch + pack_detections, pinned host tensors"}
+
+    # ---- variants: other confidence thresholds (device-resident, detect only) ---------------------
+    variants = {}
+    if not args.no_variants and rank == 0:
+        for conf in (0.25, 0.001):
+            for i in range(3):
+                step(i, conf=conf)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_it = max(5, args.steps // 3)
+            cands = 0.0
+            a.record()
+            for i in range(n_it):
+                heads, _ = dev_sets[i % N_SETS]
+                det = ops.detect_batch(heads, anchors, img, nc, conf, args.iou)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / n_it
+            cands = float(det["counts"].double().mean())
+            variants[f"conf_{conf}"] = {"decode_nms_ms": ms, "decode_nms_images_per_s": B / (ms * 1e-3),
+                                        "candidates_per_image": cands,
+                                        "kept_per_image": float(det["n_keep"].double().mean())}
+    barrier()
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+    except Exception:
+        pass
+    # loss_main_kernel: A_loss = T (grad write) + 2*rows*min(row,32) (obj sectors) + 2*P*row
+    pos = float(np.mean([sum(float((t[..., 4] > 0.5).sum()) for t in tg) for _, tg in dev_sets]))
+    a_loss = T_bytes + 2 * rows * min(row_bytes, 32) + 2 * pos * row_bytes
+    lm = kernels.get("loss_main_kernel", {"avg_ms": float("nan")})
+    achieved = a_loss / (lm["avg_ms"] * 1e-3) / 1e9
+    roofline = {"kernel": "loss_main_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "peak_source": peak_src, "algorithmic_bytes": a_loss,
+                "traffic": traffic.get("loss_main_kernel")}
+    mk = kernels.get("nms_mask_kernel", {"avg_ms": float("nan")})
+    pairs = float(np.mean(pair_counts))
+    clocks = sampler.summary()
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / 17.0 / 1e9  # Gpair/s at 17 warp-instructions per 32 pairs
+    roofline_nms = {"kernel": "nms_mask_kernel", "bound": "fp32-issue", "pairs_per_launch": pairs,
+                    "achieved": pairs / (mk["avg_ms"] * 1e-3) / 1e9, "unit": "Gpair/s", "peak": issue_peak,
+                    "frac": pairs / (mk["avg_ms"] * 1e-3) / 1e9 / issue_peak,
+                    "peak_source": "148 SM x 4 issue slots x 32 lanes x sampled SM clock / 17 instructions per pair (SASS)",
+                    "traffic": traffic.get("nms_mask_kernel")}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms, cores, sample = run_cpu_reference(args, min(B, 8), 2, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
+
+    line = {
+        "metric": METRIC, "value": B * world / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "loss_fwd_bwd_ms": loss_ms, "decode_nms_ms": det_ms, "decode_nms_images_per_s": B * world / (det_ms * 1e-3),
+        "candidates_per_image": float(np.mean(cand_counts)) / B, "kept_per_image": float(np.mean(keep_counts)) / B,
+        "e2e": e2e, "gpu_launches": int(launches), "kernels": kernels,
+        "roofline": roofline, "roofline_nms": roofline_nms, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "variants": variants,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_main(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    b200_main(args, rank, local_rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -190,6 +190,22 @@ int yb_batched_nms(const float* boxes, const float* scores, const int64_t* class
                    long long trick_max_numel, int64_t* keep, int* n_keep,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * detection list of predict()                                              train.py:1236-1246
+ *   Packs the kept detections of a batch as rows (x1, y1, x2, y2, conf, class) fp32, image after
+ *   image, each image in descending score order.  out must hold sum(n_keep)*6 floats
+ *   (<= B*cap*6); offsets (B+1) int32 receives the first row of every image and the total.
+ * ---------------------------------------------------------------------------------------- */
+int yb_pack_detections(const float* boxes, const float* scores, const int64_t* classes,
+                       const int64_t* keep, const int* n_keep, int B, int cap, float* out,
+                       int* offsets, void* stream);
+
+/* Per-launch CUDA-event timing for bench.py: when enabled every kernel launch of the library is
+ * bracketed by two events on its stream; yb_timing_collect synchronises them, writes
+ * "name count total_ms" lines into buf (NUL terminated, truncated to n) and resets. */
+void yb_timing_enable(int on);
+int yb_timing_collect(char* buf, size_t n);
+
 /* Counters for tests/bench: number of kernel launches this library has enqueued (process wide). */
 unsigned long long yb_launch_count(void);
 

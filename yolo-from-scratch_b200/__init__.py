@@ -8,10 +8,10 @@ into the reference's `train` module (install.py).
 from . import _lib
 from .ops import (batched_nms, batched_nms_padded, build_targets, ciou_loss, compute_anchor_iou,
                   decode_predictions, detect_batch, detections_to_lists, filter_candidates,
-                  loss_forward_backward, nms, yolo_loss, yolo_loss_multiscale)
+                  loss_forward_backward, nms, pack_detections, yolo_loss, yolo_loss_multiscale)
 
 __all__ = [
     "decode_predictions", "ciou_loss", "yolo_loss", "yolo_loss_multiscale", "compute_anchor_iou",
     "build_targets", "filter_candidates", "nms", "batched_nms", "batched_nms_padded", "detect_batch",
-    "detections_to_lists", "loss_forward_backward",
+    "detections_to_lists", "pack_detections", "loss_forward_backward",
 ]

@@ -42,6 +42,8 @@ SIGNATURES = {
     "yb_version": (c_int, []),
     "yb_last_error": (c_char_p, []),
     "yb_launch_count": (c_ulonglong, []),
+    "yb_timing_enable": (None, [c_int]),
+    "yb_timing_collect": (c_int, [c_char_p, c_size_t]),
     "yb_decode_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "yb_decode_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "yb_ciou_scratch_bytes": (c_size_t, [c_longlong]),
@@ -60,6 +62,8 @@ SIGNATURES = {
     "yb_nms_min_workspace_bytes": (c_size_t, [c_int, c_int]),
     "yb_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_longlong,
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yb_pack_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p]),
 }
 
 _lib = None

@@ -103,9 +103,8 @@ static int decode_launch(bool bwd, const float* pred, const float* anchors, cons
     unsigned long long cap = (unsigned long long)sm_count() * 8 * 4;
     int blocks = (int)(want < 1 ? 1 : (want < cap ? want : cap));
     cudaStream_t st = (cudaStream_t)stream;
-    if (bwd) decode_kernel<true><<<blocks, threads, 0, st>>>(a);
-    else     decode_kernel<false><<<blocks, threads, 0, st>>>(a);
-    YB_LAUNCH_CHECK(bwd ? "decode_bwd" : "decode_fwd");
+    if (bwd) YB_LAUNCH("decode_bwd_kernel", st, decode_kernel<true><<<blocks, threads, 0, st>>>(a));
+    else     YB_LAUNCH("decode_fwd_kernel", st, decode_kernel<false><<<blocks, threads, 0, st>>>(a));
     return 0;
 }
 

@@ -224,12 +224,10 @@ extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const
     a.stage_ok = smem <= 200 * 1024;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(a.tiles_per_img, d->B);
-    filter_count_kernel<<<grid, kFTile, 0, st>>>(a);
-    YB_LAUNCH_CHECK("filter_count_kernel");
+    YB_LAUNCH("filter_count_kernel", st, filter_count_kernel<<<grid, kFTile, 0, st>>>(a));
     const size_t dyn = (a.stage_ok && a.row > 8) ? smem : 0;
     if (dyn > 48 * 1024)
         YB_CUDA(cudaFuncSetAttribute(filter_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    filter_emit_kernel<<<grid, kFTile, dyn, st>>>(a);
-    YB_LAUNCH_CHECK("filter_emit_kernel");
+    YB_LAUNCH("filter_emit_kernel", st, filter_emit_kernel<<<grid, kFTile, dyn, st>>>(a));
     return 0;
 }

@@ -449,14 +449,13 @@ extern "C" int yb_ciou_fwd_bwd(const float* pred_boxes, const float* tgt_boxes, 
     if (N > 0) {
         long long want = (N + 255) / 256, cap = (long long)sm_count() * 8;
         int blocks = (int)(want < cap ? want : cap);
-        ciou_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(pred_boxes),
-                                            reinterpret_cast<const float4*>(tgt_boxes), N, eps,
-                                            reinterpret_cast<float4*>(grad_pred),
-                                            reinterpret_cast<float4*>(grad_tgt), acc);
-        YB_LAUNCH_CHECK("ciou_kernel");
+        YB_LAUNCH("ciou_kernel", st,
+                  ciou_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(pred_boxes),
+                                                      reinterpret_cast<const float4*>(tgt_boxes), N, eps,
+                                                      reinterpret_cast<float4*>(grad_pred),
+                                                      reinterpret_cast<float4*>(grad_tgt), acc));
     }
-    ciou_mean_kernel<<<1, 1, 0, st>>>(acc, N, loss_out);
-    YB_LAUNCH_CHECK("ciou_mean_kernel");
+    YB_LAUNCH("ciou_mean_kernel", st, ciou_mean_kernel<<<1, 1, 0, st>>>(acc, N, loss_out));
     return 0;
 }
 
@@ -486,10 +485,8 @@ extern "C" int yb_loss_partials(const yb_loss_desc* d, double* partials, void* w
     if (a.n_tiles == 0) return 0;
     const int sms = sm_count();
     int blocks = (int)(a.n_tiles < (uint32_t)(sms * 8) ? a.n_tiles : (uint32_t)(sms * 8));
-    loss_main_kernel<<<blocks, kTileRows, 0, st>>>(a);
-    YB_LAUNCH_CHECK("loss_main_kernel");
-    loss_positive_kernel<<<sms * 2, 256, 0, st>>>(a);
-    YB_LAUNCH_CHECK("loss_positive_kernel");
+    YB_LAUNCH("loss_main_kernel", st, loss_main_kernel<<<blocks, kTileRows, 0, st>>>(a));
+    YB_LAUNCH("loss_positive_kernel", st, loss_positive_kernel<<<sms * 2, 256, 0, st>>>(a));
     return 0;
 }
 
@@ -517,8 +514,8 @@ extern "C" int yb_loss_finalize(const yb_loss_desc* d, const double* partials, f
         any_grad |= d->grad[s] != nullptr;
     }
     const int blocks = (any_grad && f.a.n_tiles > 0) ? sm_count() : 1;
-    loss_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(f);
-    YB_LAUNCH_CHECK("loss_finalize_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    YB_LAUNCH("loss_finalize_kernel", st, loss_finalize_kernel<<<blocks, 256, 0, st>>>(f));
     return 0;
 }
 
@@ -528,7 +525,7 @@ extern "C" int yb_scale_inplace(float* x, long long n, const float* factor, void
     if (n == 0) return 0;
     long long want = (n / 4 + 255) / 256, cap = (long long)sm_count() * 8;
     int blocks = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-    scale_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, factor);
-    YB_LAUNCH_CHECK("scale_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    YB_LAUNCH("scale_kernel", st, scale_kernel<<<blocks, 256, 0, st>>>(x, n, factor));
     return 0;
 }

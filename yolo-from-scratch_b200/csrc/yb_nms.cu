@@ -665,17 +665,14 @@ extern "C" int yb_batched_nms(const float* boxes, const float* scores, const int
     a.mask_words_per_img = ((ws_bytes - L.mask) / 8 / (size_t)B) & ~(size_t)3;
     a.keep = keep; a.n_keep = n_keep;
 
-    nms_sort_kernel<<<B, kSortThreads, 0, st>>>(a);
-    YB_LAUNCH_CHECK("nms_sort_kernel");
+    YB_LAUNCH("nms_sort_kernel", st, nms_sort_kernel<<<B, kSortThreads, 0, st>>>(a));
     dim3 grid((cap + 63) / 64, B);
-    nms_mask_kernel<<<grid, kMaskThreads, 0, st>>>(a);
-    YB_LAUNCH_CHECK("nms_mask_kernel");
+    YB_LAUNCH("nms_mask_kernel", st, nms_mask_kernel<<<grid, kMaskThreads, 0, st>>>(a));
     const size_t nw_cap = ((size_t)cap + 63) / 64;
     const size_t dyn = nw_cap * 8 * 2 + nw_cap * 2 * 4;
     YB_CHECK_ARG(dyn <= 200 * 1024, "nms: cap too large for the scan kernel");
     if (dyn > 40 * 1024)
         YB_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    nms_scan_kernel<<<B, kScanThreads, dyn, st>>>(a);
-    YB_LAUNCH_CHECK("nms_scan_kernel");
+    YB_LAUNCH("nms_scan_kernel", st, nms_scan_kernel<<<B, kScanThreads, dyn, st>>>(a));
     return 0;
 }

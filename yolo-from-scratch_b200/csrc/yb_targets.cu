@@ -133,8 +133,8 @@ extern "C" int yb_anchor_iou(const float* box_wh, const float* anchors, float* i
     if (n == 0) return 0;
     YB_CHECK_ARG(box_wh && anchors && iou_out, "anchor_iou: null pointer");
     int tot = n * A;
-    anchor_iou_kernel<<<(tot + 127) / 128, 128, 0, (cudaStream_t)stream>>>(box_wh, anchors, iou_out, n, A);
-    YB_LAUNCH_CHECK("anchor_iou_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    YB_LAUNCH("anchor_iou_kernel", st, anchor_iou_kernel<<<(tot + 127) / 128, 128, 0, st>>>(box_wh, anchors, iou_out, n, A));
     return 0;
 }
 
@@ -157,7 +157,10 @@ extern "C" int yb_build_targets(const double* labels, const int* n_gt, const dou
         a.G[s] = G_host[s];
         a.tgt[s] = targets_host[s];
         size_t bytes = (size_t)B * G_host[s] * G_host[s] * A * (5 + nc) * sizeof(float);
-        YB_CUDA(cudaMemsetAsync(targets_host[s], 0, bytes, st));  // :141-145 torch.zeros
+        {
+            KernelScope ks("targets_memset", st);
+            YB_CUDA(cudaMemsetAsync(targets_host[s], 0, bytes, st));  // :141-145 torch.zeros
+        }
         count_launch();
     }
     if (status) YB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
@@ -166,7 +169,6 @@ extern "C" int yb_build_targets(const double* labels, const int* n_gt, const dou
     YB_CHECK_ARG(smem <= 200 * 1024, "build_targets: max_gt=%d too large", max_gt);
     if (smem > 48 * 1024)
         YB_CUDA(cudaFuncSetAttribute(build_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    build_targets_kernel<<<B, 128, smem, st>>>(a);
-    YB_LAUNCH_CHECK("build_targets_kernel");
+    YB_LAUNCH("build_targets_kernel", st, build_targets_kernel<<<B, 128, smem, st>>>(a));
     return 0;
 }

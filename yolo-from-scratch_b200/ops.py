@@ -499,18 +499,27 @@ def detect_batch(predictions, anchors_list, img_size, num_classes=1, conf_thresh
     return {"boxes": boxes, "scores": scores, "classes": classes, "counts": counts, "keep": keep, "n_keep": n_keep}
 
 
+def pack_detections(det):
+    """Device-side detection list: (rows (B*cap,6) fp32 [x1,y1,x2,y2,conf,class], offsets (B+1,) int32).
+    Only the first offsets[B] rows are meaningful."""
+    boxes, keep = det["boxes"], det["keep"]
+    B, cap = boxes.shape[0], boxes.shape[1]
+    with torch.cuda.device(boxes.device):
+        rows = torch.empty(B * cap, 6, dtype=torch.float32, device=boxes.device)
+        offsets = torch.zeros(B + 1, dtype=torch.int32, device=boxes.device)
+        _lib.check(_lib.lib().yb_pack_detections(boxes.data_ptr(), det["scores"].data_ptr(), det["classes"].data_ptr(),
+                                                 keep.data_ptr(), det["n_keep"].data_ptr(), B, cap, rows.data_ptr(),
+                                                 offsets.data_ptr(), _stream()), "yb_pack_detections")
+    return rows, offsets
+
+
 def detections_to_lists(det):
-    """[(x1, y1, x2, y2, conf, class_id), ...] per image (train.py:1242-1246), one D2H copy."""
+    """[(x1, y1, x2, y2, conf, class_id), ...] per image (train.py:1242-1246): one pack kernel and
+    two D2H copies instead of K*6 `.item()` syncs."""
     n_keep = det["n_keep"].cpu()
     if (n_keep < 0).any():
         raise RuntimeError("NMS workspace overflow or class id out of range")
-    out = []
-    for b in range(n_keep.numel()):
-        k = int(n_keep[b])
-        idx = det["keep"][b, :k]
-        bx = det["boxes"][b].index_select(0, idx).cpu()
-        sc = det["scores"][b].index_select(0, idx).cpu()
-        cl = det["classes"][b].index_select(0, idx).cpu()
-        out.append([(float(bx[i, 0]), float(bx[i, 1]), float(bx[i, 2]), float(bx[i, 3]), float(sc[i]), int(cl[i]))
-                    for i in range(k)])
-    return out
+    rows, offsets = pack_detections(det)
+    off = offsets.cpu().tolist()
+    host = rows[:off[-1]].cpu().tolist()
+    return [[(r[0], r[1], r[2], r[3], r[4], int(r[5])) for r in host[off[b]:off[b + 1]]] for b in range(len(off) - 1)]
