@@ -179,15 +179,24 @@ int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const float* let
  *   boxes.py:98-101), larger ones the per-class loop (boxes.py:113-120).  Pass 100000 for CUDA
  *   callers, 4000 for CPU callers, -1 to force per-class, LLONG_MAX to force the trick.
  *   Output: keep (B,cap) int64 = kept candidate indices (0..counts[b]) in descending score order,
- *   n_keep (B) int32.  Class ids must satisfy 0 <= id < 65536.
+ *   n_keep (B) int32.
+ *
+ *   algo selects how the same result is computed:
+ *     YB_NMS_GRAPH    (default) sparse suppression graph: spatial/area-ordered tile culling, edge
+ *                     list, parallel fixed-point resolve.  Workspace holds the edge list; an image
+ *                     with more edges than fit (or class ids >= 512) reports n_keep[b] = -1 and
+ *                     should be re-run with YB_NMS_BITMASK.
+ *     YB_NMS_BITMASK  dense blocked IoU bitmask + serial scan (torchvision's structure, batched);
+ *                     class ids < 65536; never overflows with yb_nms_workspace_bytes().
  * ---------------------------------------------------------------------------------------- */
-size_t yb_nms_workspace_bytes(int B, int cap);      /* worst case: never overflows */
-size_t yb_nms_min_workspace_bytes(int B, int cap);  /* fixed part; anything above it holds mask rows.
-                                                       An image whose suppression-mask rows do not fit
-                                                       reports n_keep[b] = -1 (retry with more). */
+#define YB_NMS_GRAPH 0
+#define YB_NMS_BITMASK 1
+size_t yb_nms_workspace_bytes(int B, int cap);      /* enough for either algorithm, worst case */
+size_t yb_nms_min_workspace_bytes(int B, int cap);  /* fixed part; the rest holds mask rows / edges */
+size_t yb_nms_graph_workspace_bytes(int B, int cap, int edges_per_box); /* graph algo, sized edge list */
 int yb_batched_nms(const float* boxes, const float* scores, const int64_t* classes,
                    const int* counts, int B, int cap, double iou_threshold,
-                   long long trick_max_numel, int64_t* keep, int* n_keep,
+                   long long trick_max_numel, int algo, int64_t* keep, int* n_keep,
                    void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------

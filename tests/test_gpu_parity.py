@@ -286,17 +286,22 @@ def rand_boxes(n, seed, span=300.0, neg=0.0, wmax=80.0):
     return torch.cat([xy, xy + wh], dim=1), torch.rand(n, generator=g)
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 63, 64, 65, 127, 128, 129, 255, 256, 257, 1000, 5000])
-@pytest.mark.parametrize("thr", [0.4, 0.0, 0.7])
-def test_nms_vs_oracle_and_torchvision(yb, n, thr):
+ALGOS = [0, 1]  # YB_NMS_GRAPH (sparse graph, default), YB_NMS_BITMASK (dense bitmask)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 1000, 5000])
+@pytest.mark.parametrize("thr", [0.4, 0.0, 0.7, 1.0, -0.5])
+def test_nms_vs_oracle_and_torchvision(yb, n, thr, algo):
     import torchvision
     boxes, scores = rand_boxes(n, n)
-    got = yb.nms(boxes.cuda(), scores.cuda(), thr).cpu().numpy()
+    got = yb.nms(boxes.cuda(), scores.cuda(), thr, algo=algo).cpu().numpy()
     assert np.array_equal(got, R.nms_indices(boxes.numpy(), scores.numpy(), thr, "cuda"))
     assert np.array_equal(got, torchvision.ops.nms(boxes.cuda(), scores.cuda(), thr).cpu().numpy())
 
 
-def test_nms_ties_degenerate_and_nan(yb):
+@pytest.mark.parametrize("algo", ALGOS)
+def test_nms_ties_degenerate_and_nan(yb, algo):
     import torchvision
     boxes, scores = rand_boxes(700, 5)
     scores[::5] = 0.5          # ties: lower index wins
@@ -305,20 +310,21 @@ def test_nms_ties_degenerate_and_nan(yb):
     boxes[11] = torch.tensor([5.0, 5.0, 5.0, 5.0])      # identical zero-area pair: 0/0
     boxes[12] = torch.tensor([50.0, 50.0, 20.0, 90.0])  # negative width
     boxes[13] = torch.tensor([float("nan"), 0.0, 10.0, 10.0])
-    got = yb.nms(boxes.cuda(), scores.cuda(), 0.4).cpu().numpy()
+    got = yb.nms(boxes.cuda(), scores.cuda(), 0.4, algo=algo).cpu().numpy()
     assert np.array_equal(got, torchvision.ops.nms(boxes.cuda(), scores.cuda(), 0.4).cpu().numpy())
     assert np.array_equal(got, R.nms_indices(boxes.numpy(), scores.numpy(), 0.4, "cuda"))
-    assert yb.nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), 0.5).numel() == 0
+    assert yb.nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), 0.5, algo=algo).numel() == 0
 
 
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("n,nc,neg", [(800, 4, 0.0), (800, 4, 200.0), (24000, 80, 100.0), (26000, 80, 100.0), (26000, 1, 0.0)])
-def test_batched_nms_both_regimes(yb, n, nc, neg):
+def test_batched_nms_both_regimes(yb, n, nc, neg, algo):
     """n <= 25000 uses torchvision's coordinate trick (incl. its negative-coordinate cross-class
     quirk), larger n its per-class loop (boxes.py:80)."""
     import torchvision
     boxes, scores = rand_boxes(n, n + nc, span=600.0, neg=neg, wmax=120.0)
     idxs = torch.randint(0, nc, (n,), generator=torch.Generator().manual_seed(1))
-    got = yb.batched_nms(boxes.cuda(), scores.cuda(), idxs.cuda(), 0.4).cpu().numpy()
+    got = yb.batched_nms(boxes.cuda(), scores.cuda(), idxs.cuda(), 0.4, algo=algo).cpu().numpy()
     ref = torchvision.ops.batched_nms(boxes.cuda(), scores.cuda(), idxs.cuda(), 0.4).cpu().numpy()
     assert np.array_equal(np.sort(got), np.sort(ref))
     assert np.array_equal(scores.numpy()[got], scores.numpy()[ref])
@@ -350,7 +356,8 @@ def test_nms_reference_known_answers(yb):
     assert len(run(d, 0.3)) == 1 and len(run(d, 0.7)) == 2
 
 
-def test_batched_nms_padded_varied_counts(yb):
+@pytest.mark.parametrize("algo", ALGOS)
+def test_batched_nms_padded_varied_counts(yb, algo):
     B, cap = 5, 3000
     boxes = torch.zeros(B, cap, 4)
     scores = torch.zeros(B, cap)
@@ -361,11 +368,44 @@ def test_batched_nms_padded_varied_counts(yb):
         boxes[b, :m], scores[b, :m] = bx[:m], sc[:m]
         classes[b, :m] = torch.randint(0, 3, (m,), generator=torch.Generator().manual_seed(b))
     keep, n_keep = yb.batched_nms_padded(boxes.cuda(), scores.cuda(), classes.cuda(),
-                                         torch.tensor(counts, dtype=torch.int32).cuda(), 0.4)
+                                         torch.tensor(counts, dtype=torch.int32).cuda(), 0.4, algo=algo)
     for b, m in enumerate(counts):
         want = R.batched_nms_indices(boxes[b, :m].numpy(), scores[b, :m].numpy(), classes[b, :m].numpy(), 0.4)
         assert int(n_keep[b]) == len(want)
         assert np.array_equal(keep[b, :len(want)].cpu().numpy(), want)
+
+
+def clustered_boxes(n, seed, n_clusters=40):
+    """Detector-like input: tight clusters of heavily overlapping boxes (long suppression chains)."""
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.rand(n_clusters, 2, generator=g) * 500 + 50
+    sizes = torch.rand(n_clusters, 2, generator=g) * 120 + 20
+    which = torch.randint(0, n_clusters, (n,), generator=g)
+    c = centres[which] + torch.randn(n, 2, generator=g) * 6
+    wh = sizes[which] * (1 + torch.randn(n, 2, generator=g) * 0.08).clamp(0.5, 1.5)
+    return torch.cat([c - wh / 2, c + wh / 2], dim=1), torch.rand(n, generator=g)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("n", [500, 6000])
+def test_nms_clustered_detections(yb, n, algo):
+    import torchvision
+    boxes, scores = clustered_boxes(n, n)
+    got = yb.nms(boxes.cuda(), scores.cuda(), 0.45, algo=algo).cpu().numpy()
+    assert np.array_equal(got, torchvision.ops.nms(boxes.cuda(), scores.cuda(), 0.45).cpu().numpy())
+    assert np.array_equal(got, R.nms_indices(boxes.numpy(), scores.numpy(), 0.45, "cuda"))
+
+
+def test_nms_graph_overflow_falls_back_to_bitmask(yb):
+    """3000 identical boxes: 4.5M edges do not fit the default edge list -> n_keep = -1 from the
+    graph algorithm, transparently re-run on the dense bitmask algorithm."""
+    n = 3000
+    boxes = torch.tensor([[10.0, 10.0, 50.0, 60.0]]).repeat(n, 1)
+    scores = torch.rand(n, generator=torch.Generator().manual_seed(3))
+    keep, n_keep = yb.batched_nms_padded(boxes.cuda().unsqueeze(0), scores.cuda().unsqueeze(0), None, None, 0.5)
+    assert int(n_keep[0]) == -1
+    got = yb.nms(boxes.cuda(), scores.cuda(), 0.5).cpu().numpy()
+    assert np.array_equal(got, R.nms_indices(boxes.numpy(), scores.numpy(), 0.5, "cuda")) and len(got) == 1
 
 
 # ---- end to end: the reference's predict() goldens ----------------------------------------------
@@ -427,11 +467,12 @@ def test_model_heads_fixture(yb, golden):
 
 
 # ---- full-size properties (BASELINE configs[1..3]) -----------------------------------------------
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("nc,B,conf", [(1, 64, 0.25), (80, 8, 0.001)])
-def test_full_size_properties(yb, nc, B, conf):
+def test_full_size_properties(yb, nc, B, conf, algo):
     g = torch.Generator().manual_seed(1234)
     heads = [torch.randn(B, G, G, 3, 5 + nc, generator=g).cuda() for G in (80, 40, 20)]
-    det = yb.detect_batch(heads, ANCH, 640, nc, conf, 0.4)
+    det = yb.detect_batch(heads, ANCH, 640, nc, conf, 0.4, algo=algo)
     counts, n_keep = det["counts"].cpu(), det["n_keep"].cpu()
     assert (n_keep > 0).all() and (n_keep <= counts).all()
     for b in (0, B - 1):

@@ -8,7 +8,8 @@ into the reference's `train` module (install.py).
 from . import _lib
 from .ops import (batched_nms, batched_nms_padded, build_targets, ciou_loss, compute_anchor_iou,
                   decode_predictions, detect_batch, detections_to_lists, filter_candidates,
-                  loss_forward_backward, nms, pack_detections, yolo_loss, yolo_loss_multiscale)
+                  loss_forward_backward, nms, nms_retry_overflow, pack_detections,
+                  NMS_GRAPH, NMS_BITMASK, yolo_loss, yolo_loss_multiscale)
 
 __all__ = [
     "decode_predictions", "ciou_loss", "yolo_loss", "yolo_loss_multiscale", "compute_anchor_iou",

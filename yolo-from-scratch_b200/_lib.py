@@ -11,6 +11,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_in
 
 MAX_SCALES = 4
 MAX_ANCHORS = 8
+NMS_GRAPH, NMS_BITMASK = 0, 1
 LIB_NAME = "libyolo_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
@@ -60,7 +61,8 @@ SIGNATURES = {
                                   c_int, c_void_p, c_size_t, c_void_p]),
     "yb_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
     "yb_nms_min_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "yb_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_longlong,
+    "yb_nms_graph_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "yb_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_longlong, c_int,
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_pack_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),

@@ -19,13 +19,10 @@
 //                    kept set is emitted in descending score order.
 // Bound: fp32 SIMT issue (IoU pairs/s); tensor cores do not apply.
 #include "yb_common.cuh"
+#include "yb_sort.cuh"
 
 namespace yb {
 
-typedef unsigned long long u64;
-typedef uint32_t u32;
-
-constexpr int kSortThreads = 1024;
 constexpr int kScanThreads = 1024;
 constexpr int kMaskThreads = 128;
 constexpr int kGroupTiles = 4;  // column tiles (of 64) per warp iteration
@@ -64,79 +61,6 @@ struct NmsArgs {
     int* n_keep;
 };
 
-__device__ __forceinline__ u32 desc_key(float s) {
-    s = s + 0.0f;  // -0.0 -> +0.0 : torch compares them equal
-    u32 u = __float_as_uint(s);
-    u32 asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    if (s != s) asc = 0xffffffffu;  // NaN sorts as the largest value (first when descending)
-    return ~asc;
-}
-
-// One stable LSD pass on an 8-bit digit.  Each warp owns a contiguous range of the input and a
-// private 256-bin histogram row, so ranks are exact without atomics.
-__device__ void radix_pass(const u32* __restrict__ kin, const u32* __restrict__ vin,
-                           u32* __restrict__ kout, u32* __restrict__ vout, int M, int shift,
-                           u32* hist /*[32][256]*/, u32* tot /*[256]*/) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (((M + 31) / 32) + 31) & ~31;
-    const int beg = warp * per;
-    const int end = min(beg + per, M);
-    for (int i = tid; i < 32 * 256; i += kSortThreads) hist[i] = 0;
-    __syncthreads();
-    u32* h = hist + warp * 256;
-    for (int i0 = beg; i0 < end; i0 += 32) {
-        const int i = i0 + lane;
-        const bool valid = i < end;
-        const u32 d = valid ? ((kin[i] >> shift) & 255u) : 0x1000u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (valid && lane == (__ffs(peers) - 1)) h[d] += __popc(peers);
-        __syncwarp();
-    }
-    __syncthreads();
-    if (tid < 256) {
-        u32 run = 0;
-        for (int w = 0; w < 32; ++w) {
-            const u32 t = hist[w * 256 + tid];
-            hist[w * 256 + tid] = run;
-            run += t;
-        }
-        tot[tid] = run;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        u32 v[8], s = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { v[k] = tot[lane * 8 + k]; s += v[k]; }
-        u32 inc = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += n;
-        }
-        u32 run = inc - s;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { tot[lane * 8 + k] = run; run += v[k]; }
-    }
-    __syncthreads();
-    for (int i0 = beg; i0 < end; i0 += 32) {
-        const int i = i0 + lane;
-        const bool valid = i < end;
-        const u32 key = valid ? kin[i] : 0u;
-        const u32 d = valid ? ((key >> shift) & 255u) : 0x1000u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid) {
-            const u32 dst = h[d] + tot[d] + rank;
-            kout[dst] = key;
-            vout[dst] = vin[i];
-        }
-        __syncwarp();
-        if (valid && lane == (__ffs(peers) - 1)) h[d] += __popc(peers);
-        __syncwarp();
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const NmsArgs a) {
     __shared__ u32 s_hist[32 * 256];
     __shared__ u32 s_tot[256];
@@ -145,6 +69,7 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const NmsArgs a)
     __shared__ int s_maxcls[32];
     __shared__ u32 s_scan[32];
     __shared__ u32 s_first[32];
+    __shared__ int s_skip;
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t off = (size_t)b * a.cap;
@@ -200,11 +125,14 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const NmsArgs a)
     u32 *k2 = a.k2 + off, *v2 = a.v2 + off;
     for (int i = tid; i < M; i += kSortThreads) { k0[i] = desc_key(scores[i]); v0[i] = (u32)i; }
     __syncthreads();
-    radix_pass(k0, v0, k1, v1, M, 0, s_hist, s_tot);
-    radix_pass(k1, v1, k0, v0, M, 8, s_hist, s_tot);
-    radix_pass(k0, v0, k1, v1, M, 16, s_hist, s_tot);
-    radix_pass(k1, v1, k0, v0, M, 24, s_hist, s_tot);
-    // v0[r] = original index of score rank r
+    {
+        u32 *ka = k0, *va = v0, *kb = k1, *vb = v1;
+        radix_sort(ka, va, kb, vb, M, 0, 32, s_hist, s_tot, &s_skip);
+        if (va != v0) {  // keep the documented location: v0[r] = original index of score rank r
+            for (int i = tid; i < M; i += kSortThreads) v0[i] = va[i];
+            __syncthreads();
+        }
+    }
 
     // ---- per-class mode: stable partition of the ranks by class id ----
     const u32* cls_sorted = nullptr;
@@ -212,13 +140,9 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const NmsArgs a)
     if (mode == MODE_CLASS) {
         for (int i = tid; i < M; i += kSortThreads) { k1[i] = (u32)classes[v0[i]] & 0xffffu; v1[i] = (u32)i; }
         __syncthreads();
-        radix_pass(k1, v1, k2, v2, M, 0, s_hist, s_tot);
-        if (maxcls >= 256) {
-            radix_pass(k2, v2, k1, v1, M, 8, s_hist, s_tot);
-            cls_sorted = k1; prank = v1;
-        } else {
-            cls_sorted = k2; prank = v2;
-        }
+        u32 *ka = k1, *va = v1, *kb = k2, *vb = v2;
+        radix_sort(ka, va, kb, vb, M, 0, maxcls >= 256 ? 16 : 8, s_hist, s_tot, &s_skip);
+        cls_sorted = ka; prank = va;
     }
 
     // ---- gather boxes in position order; coordinate-offset trick (boxes.py:99-101) ----
@@ -617,22 +541,38 @@ static size_t nms_worst_words(int cap) {
     return words;
 }
 
+// yb_nms_graph.cu
+size_t graph_min_workspace(int B, int cap);
+int graph_nms(const float* boxes, const float* scores, const int64_t* classes, const int* counts, int B, int cap,
+              double iou_threshold, long long trick_max_numel, int64_t* keep, int* n_keep, void* ws,
+              size_t ws_bytes, cudaStream_t st);
+
 }  // namespace yb
+
+extern "C" size_t yb_nms_graph_workspace_bytes(int B, int cap, int edges_per_box) {
+    if (B <= 0 || cap <= 0) return 256;
+    if (edges_per_box < 1) edges_per_box = 1;
+    return yb::graph_min_workspace(B, cap) + (size_t)B * cap * (size_t)edges_per_box * 8 + 256;
+}
 
 extern "C" size_t yb_nms_workspace_bytes(int B, int cap) {
     if (B <= 0 || cap <= 0) return 256;
     yb::NmsLayout L = yb::nms_layout(B, cap);
-    return L.total + (size_t)B * yb::nms_worst_words(cap) * 8 + 256;
+    size_t dense = L.total + (size_t)B * yb::nms_worst_words(cap) * 8 + 256;
+    size_t graph = yb_nms_graph_workspace_bytes(B, cap, 16);
+    return dense > graph ? dense : graph;
 }
 
 extern "C" size_t yb_nms_min_workspace_bytes(int B, int cap) {
     if (B <= 0 || cap <= 0) return 256;
-    return yb::nms_layout(B, cap).total + (size_t)B * 32;
+    size_t dense = yb::nms_layout(B, cap).total + (size_t)B * 32;
+    size_t graph = yb::graph_min_workspace(B, cap);
+    return dense > graph ? dense : graph;
 }
 
 extern "C" int yb_batched_nms(const float* boxes, const float* scores, const int64_t* classes,
                               const int* counts, int B, int cap, double iou_threshold,
-                              long long trick_max_numel, int64_t* keep, int* n_keep, void* ws,
+                              long long trick_max_numel, int algo, int64_t* keep, int* n_keep, void* ws,
                               size_t ws_bytes, void* stream) {
     using namespace yb;
     YB_CHECK_ARG(B >= 0 && cap >= 0, "nms: bad B/cap");
@@ -647,6 +587,10 @@ extern "C" int yb_batched_nms(const float* boxes, const float* scores, const int
     YB_CHECK_ARG(aligned16(boxes) && aligned16(ws), "nms: boxes/workspace must be 16-byte aligned");
     YB_CHECK_ARG(B <= 65535, "nms: B too large");
     YB_CHECK_ARG(cap <= 400000, "nms: cap too large");
+    YB_CHECK_ARG(algo == YB_NMS_GRAPH || algo == YB_NMS_BITMASK, "nms: unknown algo %d", algo);
+    if (algo == YB_NMS_GRAPH)
+        return graph_nms(boxes, scores, classes, counts, B, cap, iou_threshold, trick_max_numel, keep, n_keep, ws,
+                         ws_bytes, st);
     NmsLayout L = nms_layout(B, cap);
     YB_CHECK_ARG(ws_bytes >= L.total + (size_t)B * 32, "nms: workspace too small (%zu < %zu)", ws_bytes, L.total + (size_t)B * 32);
     char* w = reinterpret_cast<char*>(ws);

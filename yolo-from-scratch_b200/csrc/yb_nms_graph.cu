@@ -1,0 +1,513 @@
+// yb_nms_graph.cu — K5 (default algorithm): exact greedy NMS as a sparse suppression graph.
+// Reference semantics: torchvision.ops.batched_nms as called by predict(), train.py:1232-1233 —
+// same arithmetic, same tie-break, same kept set as yb_nms.cu (the dense bitmask algorithm, kept
+// for dense graphs) and as torchvision's CUDA kernel; what changes is how much work is done.
+//
+// Greedy NMS keeps box j iff no KEPT box i with a higher score has IoU(i,j) > thr.  Two facts:
+//   1. IoU(i,j) > thr >= 0 needs the boxes to overlap by at least thr of the wider/taller one
+//      and their areas to be within a factor thr of each other, so after ordering the boxes by
+//      (class, area octave-pair, Morton code of the centre) almost all 32x32 tile pairs can be
+//      rejected from their bounding boxes alone, and most rows of the surviving pairs too;
+//   2. the edges that remain are few (about 1-3 per box on dense random heads), and the greedy
+//      result is the unique fixed point of  "kept <=> every higher-scored neighbour is
+//      suppressed; suppressed <=> some higher-scored neighbour is kept", reached by parallel
+//      rounds (8 rounds on 25,200 random boxes).
+// Three launches for a whole batch:
+//   graph_sort_kernel     one CTA per image: stable score sort (rank), spatial sort (position),
+//                         gather of (offset) boxes, per-tile bounding statistics
+//   graph_edge_kernel     persistent warps, one row tile at a time: tile-pair culling, row culling,
+//                         IoU > thr decided with the division-free margin test (ambiguous lanes
+//                         redo torchvision's exact fma/div arithmetic with the higher-scored box
+//                         as `a`), warp-aggregated append of directed edges (rank_hi -> rank_lo)
+//   graph_resolve_kernel  one CTA per image: fixed-point rounds over the edge list in shared-memory
+//                         bitmaps, then ordered emission of the kept indices by score rank
+// Bound: fp32 SIMT issue on the pair evaluations that survive culling.
+#include "yb_common.cuh"
+#include "yb_sort.cuh"
+
+namespace yb {
+
+constexpr int kTile = 32;
+constexpr int kEdgeThreads = 256;
+constexpr int kResolveThreads = 1024;
+
+enum { G_PLAIN = 0, G_TRICK = 1, G_CLASS = 2 };
+
+struct GImg {
+    int M, mode, exact, overflow;
+    int n_tiles;
+    u32 n_edges;
+    float s_off, t2;  // coordinate offset step; pruning threshold thr*(1-2^-10) (or -1: no pruning)
+};
+
+struct GArgs {
+    const float4* boxes;
+    const float* scores;
+    const int64_t* classes;
+    const int* counts;
+    int B, cap, tcap;
+    float thr;
+    int thr_fast_ok;
+    long long trick_max_numel;
+    u32 *k0, *v0, *k1, *v1, *k2, *v2;  // (B,cap); v0[r] = original index of score rank r
+    float4* sboxes;                    // (B,cap) boxes in position order (offset applied)
+    u32* srank;                        // (B,cap) position -> score rank
+    u32* scls;                         // (B,cap) position -> class id (per-class mode)
+    float4* tstat;                     // (B,tcap,2) tile bbox | {amin, amax, cmin, cmax}
+    GImg* info;
+    u32* ticket;
+    uint2* edges;
+    u64 edges_per_img;
+    int64_t* keep;
+    int* n_keep;
+};
+
+__device__ __forceinline__ u32 spread8(u32 v) {  // 8 bits -> even bit positions of 16
+    v = (v | (v << 4)) & 0x0f0fu;
+    v = (v | (v << 2)) & 0x3333u;
+    v = (v | (v << 1)) & 0x5555u;
+    return v;
+}
+
+__device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float* s32, int lane, int warp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float n = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, n) : fminf(v, n);
+    }
+    __syncthreads();
+    if (lane == 0) s32[warp] = v;
+    __syncthreads();
+    float r = s32[0];
+    for (int w = 1; w < 32; ++w) r = is_max ? fmaxf(r, s32[w]) : fminf(r, s32[w]);
+    return r;
+}
+
+__global__ void __launch_bounds__(kSortThreads) graph_sort_kernel(const GArgs a) {
+    __shared__ u32 s_hist[32 * 256];
+    __shared__ u32 s_tot[256];
+    __shared__ float s_f[32];
+    __shared__ int s_flag[32];
+    __shared__ int s_maxcls[32];
+    __shared__ int s_skip;
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t off = (size_t)b * a.cap;
+    int M = a.counts ? a.counts[b] : a.cap;
+    M = M < 0 ? 0 : (M > a.cap ? a.cap : M);
+    GImg* info = a.info + b;
+    if (M == 0) {
+        if (tid == 0) {
+            GImg z = {0, G_PLAIN, 0, 0, 0, 0u, 0.0f, -1.0f};
+            *info = z;
+        }
+        return;
+    }
+    const float4* boxes = a.boxes + off;
+    const float* scores = a.scores + off;
+    const int64_t* classes = a.classes ? a.classes + off : nullptr;
+    const int mode = !classes ? G_PLAIN : ((long long)M * 4 <= a.trick_max_numel ? G_TRICK : G_CLASS);
+
+    // ---- reductions ---------------------------------------------------------------------------
+    float mx = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
+    int bad = 0, maxcls = 0;
+    for (int i = tid; i < M; i += kSortThreads) {
+        const float4 q = boxes[i];
+        mx = fmaxf(mx, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+        const bool nan = (q.x != q.x) || (q.y != q.y) || (q.z != q.z) || (q.w != q.w);
+        const float big = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w)));
+        bad |= (nan ? 4 : 0) | ((nan || !(big <= 1e17f) || !(q.z >= q.x) || !(q.w >= q.y)) ? 1 : 0);
+        const float cx = (q.x + q.z) * 0.5f, cy = (q.y + q.w) * 0.5f;
+        cmin = fminf(cmin, fminf(cx, cy));
+        cmax = fmaxf(cmax, fmaxf(cx, cy));
+        if (classes) {
+            const long long c = classes[i];
+            bad |= (c < 0 || c >= 512) ? 2 : 0;
+            maxcls = max(maxcls, (int)(c & 0x1ff));
+        }
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    maxcls = __reduce_max_sync(0xffffffffu, maxcls);
+    if (lane == 0) { s_flag[warp] = bad; s_maxcls[warp] = maxcls; }
+    mx = block_reduce_minmax(mx, true, s_f, lane, warp);
+    cmin = block_reduce_minmax(cmin, false, s_f, lane, warp);
+    cmax = block_reduce_minmax(cmax, true, s_f, lane, warp);
+    bad = 0; maxcls = 0;
+    for (int w = 0; w < 32; ++w) { bad |= s_flag[w]; maxcls = max(maxcls, s_maxcls[w]); }
+    float s_off = mx + 1.0f;                            // boxes.py:99
+    if (bad & 4) s_off = __int_as_float(0x7fc00000);    // torch max propagates NaN
+    if (mode == G_TRICK && !((float)maxcls * s_off + fabsf(mx) <= 1e17f)) bad |= 1;
+    const bool exact = (bad & 1) || !a.thr_fast_ok;
+
+    // ---- stable descending score sort: v0[r] = original index ------------------------------------
+    u32 *k0 = a.k0 + off, *v0 = a.v0 + off, *k1 = a.k1 + off, *v1 = a.v1 + off;
+    u32 *k2 = a.k2 + off, *v2 = a.v2 + off;
+    for (int i = tid; i < M; i += kSortThreads) { k0[i] = desc_key(scores[i]); v0[i] = (u32)i; }
+    __syncthreads();
+    {
+        u32 *ka = k0, *va = v0, *kb = k1, *vb = v1;
+        radix_sort(ka, va, kb, vb, M, 0, 32, s_hist, s_tot, &s_skip);
+        if (va != v0) {
+            for (int i = tid; i < M; i += kSortThreads) v0[i] = va[i];
+            __syncthreads();
+        }
+    }
+
+    // ---- spatial order: (class | area octave pair | Morton(centre)) ---------------------------------
+    const float qs = (cmax > cmin) ? 255.0f / (cmax - cmin) : 0.0f;
+    for (int r = tid; r < M; r += kSortThreads) {
+        const u32 idx = v0[r];
+        const float4 q = boxes[idx];
+        const float area = (q.z - q.x) * (q.w - q.y);
+        const u32 bucket = (__float_as_uint(area) >> 24) & 0x7fu;
+        const float fx = fminf(fmaxf(((q.x + q.z) * 0.5f - cmin) * qs, 0.0f), 255.0f);
+        const float fy = fminf(fmaxf(((q.y + q.w) * 0.5f - cmin) * qs, 0.0f), 255.0f);
+        const u32 mort = spread8((u32)fx) | (spread8((u32)fy) << 1);
+        const u32 c = classes ? ((u32)classes[idx] & 0x1ffu) : 0u;
+        k1[r] = (c << 23) | (bucket << 16) | mort;
+        v1[r] = (u32)r;
+    }
+    __syncthreads();
+    u32 *ka = k1, *va = v1, *kb = k2, *vb = v2;
+    radix_sort(ka, va, kb, vb, M, 0, 32, s_hist, s_tot, &s_skip);
+
+    // ---- gather in position order; coordinate-offset trick (boxes.py:99-101) -------------------------
+    float4* sb = a.sboxes + off;
+    u32* srank = a.srank + off;
+    u32* scls = a.scls + off;
+    for (int p = tid; p < M; p += kSortThreads) {
+        const u32 r = va[p];
+        const u32 idx = v0[r];
+        float4 q = boxes[idx];
+        u32 c = 0;
+        if (classes) c = (u32)classes[idx];
+        if (mode == G_TRICK) {
+            const float o = (float)classes[idx] * s_off;
+            q.x += o; q.y += o; q.z += o; q.w += o;
+        }
+        sb[p] = q;
+        srank[p] = r;
+        scls[p] = (mode == G_CLASS) ? c : 0u;
+    }
+    __syncthreads();
+
+    // ---- tile statistics -----------------------------------------------------------------------------
+    const int n_tiles = (M + kTile - 1) / kTile;
+    float4* ts = a.tstat + (size_t)b * a.tcap * 2;
+    for (int t = warp; t < n_tiles; t += kSortThreads / 32) {
+        const int p = t * kTile + lane;
+        float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY, amin = INFINITY, amax = -INFINITY;
+        u32 c0 = 0xffffffffu, c1 = 0u;
+        if (p < M) {
+            const float4 q = sb[p];
+            x1 = q.x; y1 = q.y; x2 = q.z; y2 = q.w;
+            amin = amax = (q.z - q.x) * (q.w - q.y);
+            c0 = c1 = scls[p];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+            x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o));
+            y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+            amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
+            c1 = max(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+        }
+        if (lane == 0) {
+            ts[t * 2 + 0] = make_float4(x1, y1, x2, y2);
+            ts[t * 2 + 1] = make_float4(amin, amax, __uint_as_float(c0), __uint_as_float(c1));
+        }
+    }
+    if (tid == 0) {
+        GImg o;
+        o.M = M; o.mode = mode; o.exact = exact ? 1 : 0;
+        o.overflow = (bad & 2) ? 2 : 0;
+        o.n_tiles = n_tiles; o.n_edges = 0u; o.s_off = s_off;
+        o.t2 = exact ? -1.0f : a.thr * (1.0f - 9.765625e-4f);
+        *info = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge discovery
+// ------------------------------------------------------------------------------------------------
+struct RowAux { float area; u32 rank; u32 cls; u32 pad; };
+
+__global__ void __launch_bounds__(kEdgeThreads) graph_edge_kernel(const GArgs a) {
+    __shared__ float4 s_row[kEdgeThreads / 32][kTile];
+    __shared__ RowAux s_aux[kEdgeThreads / 32][kTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const u32 total = (u32)a.tcap * (u32)a.B;
+    const float kEps = 9.5367431640625e-07f;     // 2^-20
+    const float kTiny = 7.888609052210118e-31f;  // 2^-100
+    const float far = 3.0e38f;
+
+    for (;;) {
+        u32 item = 0;
+        if (lane == 0) item = atomicAdd(a.ticket, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        const int I = (int)(item / (u32)a.B), b = (int)(item % (u32)a.B);  // all images' tile 0 first
+        const GImg info = a.info[b];
+        if (I >= info.n_tiles || info.overflow) continue;
+        const int M = info.M;
+        const size_t off = (size_t)b * a.cap;
+        const float4* sb = a.sboxes + off;
+        const u32* srank = a.srank + off;
+        const u32* scls = a.scls + off;
+        const float4* ts = a.tstat + (size_t)b * a.tcap * 2;
+        uint2* edges = a.edges + (u64)b * a.edges_per_img;
+        const bool prune = info.t2 >= 0.0f;
+        const float t2 = info.t2;
+        const bool class_mode = info.mode == G_CLASS;
+
+        // this lane's row of tile I
+        const int rp = I * kTile + lane;
+        const bool rvalid = rp < M;
+        float4 rq = make_float4(-far, -far, -far, -far);
+        u32 rrank = 0xffffffffu, rcls = 0u;
+        if (rvalid) { rq = sb[rp]; rrank = srank[rp]; rcls = scls[rp]; }
+        const float rw = rq.z - rq.x, rh = rq.w - rq.y;
+        const float rS = rw * rh;
+        __syncwarp();
+        s_row[warp][lane] = rq;
+        s_aux[warp][lane] = RowAux{rS, rrank, rcls, 0u};
+        __syncwarp();
+        const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
+        const u32 icmax = __float_as_uint(ia.w);
+
+        for (int J0 = I; J0 < info.n_tiles; J0 += 32) {
+            const int Jl = J0 + lane;
+            bool ok = Jl < info.n_tiles;
+            float4 jb = make_float4(0.f, 0.f, 0.f, 0.f), ja = jb;
+            if (ok) { jb = ts[Jl * 2]; ja = ts[Jl * 2 + 1]; }
+            if (class_mode) {
+                // tiles are ordered by class: nothing beyond the last tile that can hold icmax
+                const bool beyond = ok && __float_as_uint(ja.z) > icmax;
+                ok = ok && !beyond && __float_as_uint(ja.w) >= __float_as_uint(ia.z);
+                if (__ballot_sync(0xffffffffu, beyond) == 0xffffffffu) break;
+            }
+            if (ok && prune) {
+                ok = fminf(ib.z, jb.z) > fmaxf(ib.x, jb.x) && fminf(ib.w, jb.w) > fmaxf(ib.y, jb.y) &&
+                     ia.y >= t2 * ja.x && ja.y >= t2 * ia.x;
+            }
+            unsigned cand = __ballot_sync(0xffffffffu, ok);
+            while (cand) {
+                const int jl = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                const int J = J0 + jl;
+                // tile J statistics, broadcast from the lane that tested it
+                const float jx1 = __shfl_sync(0xffffffffu, jb.x, jl), jy1 = __shfl_sync(0xffffffffu, jb.y, jl);
+                const float jx2 = __shfl_sync(0xffffffffu, jb.z, jl), jy2 = __shfl_sync(0xffffffffu, jb.w, jl);
+                const float jamin = __shfl_sync(0xffffffffu, ja.x, jl), jamax = __shfl_sync(0xffffffffu, ja.y, jl);
+                // this lane's column of tile J
+                const int cp = J * kTile + lane;
+                const bool cvalid = cp < M;
+                float4 cq = make_float4(far, far, far, far);
+                u32 crank = 0xffffffffu, ccls = 0u;
+                if (cvalid) { cq = sb[cp]; crank = srank[cp]; ccls = scls[cp]; }
+                const float cw = cq.z - cq.x, ch = cq.w - cq.y;
+                const float cS = cw * ch;
+                // row culling: lane <-> row of tile I against the bounding box of tile J
+                bool rok = rvalid;
+                if (prune) {
+                    const float ox = fminf(rq.z, jx2) - fmaxf(rq.x, jx1);
+                    const float oy = fminf(rq.w, jy2) - fmaxf(rq.y, jy1);
+                    rok = rok && ox > 0.0f && oy > 0.0f && ox >= t2 * rw && oy >= t2 * rh && jamax >= t2 * rS &&
+                          rS >= t2 * jamin;
+                }
+                unsigned rows = __ballot_sync(0xffffffffu, rok);
+                while (rows) {
+                    const int i = __ffs(rows) - 1;
+                    rows &= rows - 1u;
+                    const float4 r = s_row[warp][i];
+                    const RowAux ra = s_aux[warp][i];
+                    const float left = fmaxf(r.x, cq.x), right = fminf(r.z, cq.z);
+                    const float top = fmaxf(r.y, cq.y), bottom = fminf(r.w, cq.w);
+                    const float w = fmaxf(right - left, 0.0f), h = fmaxf(bottom - top, 0.0f);
+                    const float inter = w * h;
+                    bool pr, need_exact = info.exact != 0;
+                    if (!need_exact) {
+                        // row taken as `a`; the true roles change den by <= 2 ulp, inside the margin
+                        const float den = __fmaf_rn(cw, ch, ra.area) - inter;
+                        const float tt = a.thr * den;
+                        const float d = inter - tt;
+                        pr = d > 0.0f;
+                        need_exact = !(fabsf(d) > __fmaf_rn(tt, kEps, kTiny));
+                    }
+                    if (need_exact) {
+                        // torchvision devIoU with a = the higher-scored box
+                        const bool row_a = ra.rank < crank;
+                        const float sa = row_a ? ra.area : cS;
+                        const float bw = row_a ? cw : (r.z - r.x), bh = row_a ? ch : (r.w - r.y);
+                        const float den = __fmaf_rn(bw, bh, sa) - inter;
+                        pr = (inter / den) > a.thr;
+                    }
+                    if (__ballot_sync(0xffffffffu, pr) == 0u) continue;
+                    // rare: an edge.  Validity, same class (per-class mode), each unordered pair once.
+                    bool fin = pr && cvalid && (!class_mode || ccls == ra.cls) && (J != I || lane > i);
+                    const unsigned em = __ballot_sync(0xffffffffu, fin);
+                    if (em) {
+                        const int leader = __ffs(em) - 1;
+                        u32 base = 0;
+                        if (lane == leader) base = atomicAdd(&a.info[b].n_edges, (u32)__popc(em));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (fin) {
+                            const u64 k = (u64)base + __popc(em & lt_mask);
+                            if (k < a.edges_per_img) edges[k] = make_uint2(min(ra.rank, crank), max(ra.rank, crank));
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-point resolve + emit
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GArgs a) {
+    extern __shared__ u32 s_bits[];  // U | K | fK | fU, each nw words
+    __shared__ u32 s_scan[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GImg info = a.info[b];
+    const int M = info.M;
+    if (M == 0) {
+        if (tid == 0) a.n_keep[b] = 0;
+        return;
+    }
+    if (info.overflow || (u64)info.n_edges > a.edges_per_img) {
+        if (tid == 0) a.n_keep[b] = -1;
+        return;
+    }
+    const int nw = (M + 31) >> 5;
+    const int nw_cap = (a.cap + 31) >> 5;
+    u32 *U = s_bits, *K = s_bits + nw_cap, *fK = s_bits + 2 * nw_cap, *fU = s_bits + 3 * nw_cap;
+    for (int w = tid; w < nw; w += kResolveThreads) {
+        const int rem = M - w * 32;
+        U[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+        K[w] = 0u; fK[w] = 0u; fU[w] = 0u;
+    }
+    const uint2* edges = a.edges + (u64)b * a.edges_per_img;
+    const u32 E = info.n_edges;
+    __syncthreads();
+    for (;;) {
+        for (u32 e = tid; e < E; e += kResolveThreads) {
+            const uint2 sd = edges[e];  // x = higher-scored (lower rank), y = lower-scored
+            const u32 dw = sd.y >> 5, dbit = 1u << (sd.y & 31);
+            if (U[dw] & dbit) {
+                const u32 sw = sd.x >> 5, sbit = 1u << (sd.x & 31);
+                if (K[sw] & sbit) atomicOr(&fK[dw], dbit);
+                else if (U[sw] & sbit) atomicOr(&fU[dw], dbit);
+            }
+        }
+        __syncthreads();
+        int left = 0;
+        for (int w = tid; w < nw; w += kResolveThreads) {
+            const u32 u = U[w];
+            const u32 sup = u & fK[w];
+            const u32 kept = u & ~fK[w] & ~fU[w];
+            const u32 nu = u & ~(sup | kept);
+            U[w] = nu;
+            K[w] |= kept;
+            fK[w] = 0u; fU[w] = 0u;
+            left |= nu != 0u;
+        }
+        if (!__syncthreads_or(left)) break;
+    }
+    // ---- emit kept indices in descending score order (K is indexed by score rank) ----
+    const u32* order = a.v0 + (size_t)b * a.cap;
+    const int chunk = (nw + kResolveThreads - 1) / kResolveThreads;
+    const int c0 = min(tid * chunk, nw), c1 = min(c0 + chunk, nw);
+    u32 sum = 0;
+    for (int w = c0; w < c1; ++w) sum += __popc(K[w]);
+    u32 inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    u32 base = inc - sum, total = 0;
+    for (int w = 0; w < 32; ++w) {
+        if (w < warp) base += s_scan[w];
+        total += s_scan[w];
+    }
+    int64_t* keep = a.keep + (size_t)b * a.cap;
+    for (int w = c0; w < c1; ++w) {
+        u32 bits = K[w];
+        while (bits) {
+            const int j = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            keep[base++] = (int64_t)order[w * 32 + j];
+        }
+    }
+    if (tid == 0) a.n_keep[b] = (int)total;
+}
+
+// ---- host side -------------------------------------------------------------------------------
+struct GLayout {
+    size_t k[6], sboxes, srank, scls, tstat, info, ticket, edges, total;
+};
+
+static inline size_t g_align(size_t x) { return (x + 255) / 256 * 256; }
+
+static GLayout graph_layout(int B, int cap) {
+    GLayout L;
+    size_t o = 0;
+    const size_t n = (size_t)B * cap;
+    const size_t tcap = ((size_t)cap + kTile - 1) / kTile;
+    for (int i = 0; i < 6; ++i) { L.k[i] = o; o = g_align(o + n * 4); }
+    L.sboxes = o; o = g_align(o + n * 16);
+    L.srank = o; o = g_align(o + n * 4);
+    L.scls = o; o = g_align(o + n * 4);
+    L.tstat = o; o = g_align(o + (size_t)B * tcap * 32);
+    L.info = o; o = g_align(o + (size_t)B * sizeof(GImg));
+    L.ticket = o; o = g_align(o + 256);
+    L.edges = o;
+    L.total = o;
+    return L;
+}
+
+size_t graph_min_workspace(int B, int cap) { return graph_layout(B, cap).total + (size_t)B * 8; }
+
+int graph_nms(const float* boxes, const float* scores, const int64_t* classes, const int* counts, int B, int cap,
+              double iou_threshold, long long trick_max_numel, int64_t* keep, int* n_keep, void* ws,
+              size_t ws_bytes, cudaStream_t st) {
+    GLayout L = graph_layout(B, cap);
+    YB_CHECK_ARG(ws_bytes >= L.total + (size_t)B * 8, "nms(graph): workspace too small (%zu < %zu)", ws_bytes,
+                 L.total + (size_t)B * 8);
+    char* w = reinterpret_cast<char*>(ws);
+    GArgs a;
+    a.boxes = reinterpret_cast<const float4*>(boxes); a.scores = scores; a.classes = classes; a.counts = counts;
+    a.B = B; a.cap = cap; a.tcap = (cap + kTile - 1) / kTile;
+    a.thr = (float)iou_threshold;
+    a.thr_fast_ok = (a.thr >= 0.0f && a.thr <= 1e30f) ? 1 : 0;
+    a.trick_max_numel = trick_max_numel;
+    a.k0 = (u32*)(w + L.k[0]); a.v0 = (u32*)(w + L.k[1]); a.k1 = (u32*)(w + L.k[2]);
+    a.v1 = (u32*)(w + L.k[3]); a.k2 = (u32*)(w + L.k[4]); a.v2 = (u32*)(w + L.k[5]);
+    a.sboxes = (float4*)(w + L.sboxes); a.srank = (u32*)(w + L.srank); a.scls = (u32*)(w + L.scls);
+    a.tstat = (float4*)(w + L.tstat);
+    a.info = (GImg*)(w + L.info);
+    a.ticket = (u32*)(w + L.ticket);
+    a.edges = (uint2*)(w + L.edges);
+    a.edges_per_img = (ws_bytes - L.edges) / 8 / (size_t)B;
+    a.keep = keep; a.n_keep = n_keep;
+
+    YB_CUDA(cudaMemsetAsync(a.ticket, 0, 256, st));
+    YB_LAUNCH("graph_sort_kernel", st, graph_sort_kernel<<<B, kSortThreads, 0, st>>>(a));
+    const int ctas = sm_count() * 4;
+    YB_LAUNCH("graph_edge_kernel", st, graph_edge_kernel<<<ctas, kEdgeThreads, 0, st>>>(a));
+    const size_t dyn = (size_t)((cap + 31) / 32) * 4 * 4;
+    YB_CHECK_ARG(dyn <= 200 * 1024, "nms(graph): cap too large for the resolve kernel");
+    if (dyn > 40 * 1024)
+        YB_CUDA(cudaFuncSetAttribute(graph_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    YB_LAUNCH("graph_resolve_kernel", st, graph_resolve_kernel<<<B, kResolveThreads, dyn, st>>>(a));
+    return 0;
+}
+
+}  // namespace yb

@@ -422,19 +422,17 @@ def filter_candidates(predictions, anchors_list, img_size, num_classes=1, conf_t
     return boxes, scores, classes, counts
 
 
-_nms_ws_cache = {}
+NMS_GRAPH, NMS_BITMASK = _lib.NMS_GRAPH, _lib.NMS_BITMASK
+GRAPH_EDGES_PER_BOX = 16  # edge-list capacity of the default workspace (dense random heads need ~3)
 
 
-def _nms_workspace(B, cap, dev, full):
-    L = _lib.lib()
-    need = L.yb_nms_workspace_bytes(B, cap) if full else min(
-        L.yb_nms_workspace_bytes(B, cap), L.yb_nms_min_workspace_bytes(B, cap) + (256 << 20))
-    return torch.empty(need, dtype=torch.uint8, device=dev)
-
-
-def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel=TRICK_MAX_NUMEL_CUDA):
+def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel=TRICK_MAX_NUMEL_CUDA,
+                       algo=NMS_GRAPH):
     """NMS for B images at once.  boxes (B,cap,4), scores (B,cap), classes (B,cap) int64 or None,
-    counts (B,) int32 or None.  Returns (keep (B,cap) int64, n_keep (B,) int32) on the GPU."""
+    counts (B,) int32 or None.  Returns (keep (B,cap) int64, n_keep (B,) int32) on the GPU, nothing
+    synchronised.  With the default sparse-graph algorithm an image whose suppression graph does
+    not fit the workspace reports n_keep = -1; `nms_retry_overflow` re-runs those on the dense
+    bitmask algorithm (detections_to_lists / batched_nms do that for you)."""
     dev = boxes.device
     B, cap = boxes.shape[0], boxes.shape[1]
     L = _lib.lib()
@@ -442,14 +440,32 @@ def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_
     n_keep = torch.zeros(B, dtype=torch.int32, device=dev)
     if B == 0 or cap == 0:
         return keep, n_keep
-    ws = _nms_workspace(B, cap, dev, full=True)
+    need = (L.yb_nms_graph_workspace_bytes(B, cap, GRAPH_EDGES_PER_BOX) if algo == NMS_GRAPH
+            else L.yb_nms_workspace_bytes(B, cap))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
     _lib.check(L.yb_batched_nms(boxes.data_ptr(), scores.data_ptr(), _ptr(classes), _ptr(counts), B, cap,
-                                float(iou_threshold), int(trick_max_numel), keep.data_ptr(), n_keep.data_ptr(),
-                                ws.data_ptr(), ws.numel(), _stream()), "yb_batched_nms")
+                                float(iou_threshold), int(trick_max_numel), int(algo), keep.data_ptr(),
+                                n_keep.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "yb_batched_nms")
     return keep, n_keep
 
 
-def _nms_single(boxes, scores, idxs, iou_threshold):
+def nms_retry_overflow(boxes, scores, classes, counts, iou_threshold, trick_max_numel, keep, n_keep):
+    """Re-run, with the dense bitmask algorithm, the images the graph algorithm gave up on
+    (n_keep == -1).  Synchronises (reads n_keep).  Returns (keep, n_keep), updated in place."""
+    bad = (n_keep < 0).nonzero().flatten()
+    if bad.numel() == 0:
+        return keep, n_keep
+    sel = lambda t: None if t is None else t.index_select(0, bad).contiguous()
+    k2, n2 = batched_nms_padded(sel(boxes), sel(scores), sel(classes), sel(counts), iou_threshold, trick_max_numel,
+                                algo=NMS_BITMASK)
+    if bool((n2 < 0).any()):
+        raise ValueError("batched_nms: class ids must be in [0, 65536)")
+    keep.index_copy_(0, bad, k2)
+    n_keep.index_copy_(0, bad, n2)
+    return keep, n_keep
+
+
+def _nms_single(boxes, scores, idxs, iou_threshold, algo=NMS_GRAPH):
     if boxes.dim() != 2 or boxes.shape[1] != 4:
         raise ValueError("boxes must be (N,4)")
     dev = _device()
@@ -465,27 +481,28 @@ def _nms_single(boxes, scores, idxs, iou_threshold):
             c = idxs.detach().to(dev, torch.int64).contiguous().unsqueeze(0)
         # torchvision picks its algorithm from the caller's device (boxes.py:80)
         trick = TRICK_MAX_NUMEL_CPU if orig_dev.type == "cpu" else TRICK_MAX_NUMEL_CUDA
-        keep, n_keep = batched_nms_padded(b, s, c, None, iou_threshold, trick)
+        keep, n_keep = batched_nms_padded(b, s, c, None, iou_threshold, trick, algo)
         k = int(n_keep[0].item())
         if k < 0:
-            raise ValueError("batched_nms: class ids must be in [0, 65536)")
+            keep, n_keep = nms_retry_overflow(b, s, c, None, iou_threshold, trick, keep, n_keep)
+            k = int(n_keep[0].item())
         out = keep[0, :k].clone()
     return out if orig_dev == dev else out.to(orig_dev)
 
 
-def batched_nms(boxes, scores, idxs, iou_threshold):
+def batched_nms(boxes, scores, idxs, iou_threshold, algo=NMS_GRAPH):
     """Drop-in for torchvision.ops.batched_nms (train.py:1232-1233): int64 indices of the kept
     boxes in descending score order."""
-    return _nms_single(boxes, scores, idxs, iou_threshold)
+    return _nms_single(boxes, scores, idxs, iou_threshold, algo)
 
 
-def nms(boxes, scores, iou_threshold):
+def nms(boxes, scores, iou_threshold, algo=NMS_GRAPH):
     """Drop-in for torchvision.ops.nms."""
-    return _nms_single(boxes, scores, None, iou_threshold)
+    return _nms_single(boxes, scores, None, iou_threshold, algo)
 
 
 def detect_batch(predictions, anchors_list, img_size, num_classes=1, conf_threshold=0.5, iou_threshold=0.4,
-                 letterbox=None, trick_max_numel=TRICK_MAX_NUMEL_CUDA):
+                 letterbox=None, trick_max_numel=TRICK_MAX_NUMEL_CUDA, algo=NMS_GRAPH):
     """predict() lines 1152-1238 for a whole batch on the GPU: decode + filter + global NMS.
 
     Returns a dict of device tensors: boxes (B,cap,4), scores, classes, counts (candidates per
@@ -495,8 +512,9 @@ def detect_batch(predictions, anchors_list, img_size, num_classes=1, conf_thresh
     boxes, scores, classes, counts = filter_candidates(predictions, anchors_list, img_size, num_classes,
                                                        conf_threshold, letterbox)
     with torch.cuda.device(boxes.device):
-        keep, n_keep = batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel)
-    return {"boxes": boxes, "scores": scores, "classes": classes, "counts": counts, "keep": keep, "n_keep": n_keep}
+        keep, n_keep = batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel, algo)
+    return {"boxes": boxes, "scores": scores, "classes": classes, "counts": counts, "keep": keep, "n_keep": n_keep,
+            "iou_threshold": float(iou_threshold), "trick_max_numel": int(trick_max_numel)}
 
 
 def pack_detections(det):
@@ -516,9 +534,9 @@ def pack_detections(det):
 def detections_to_lists(det):
     """[(x1, y1, x2, y2, conf, class_id), ...] per image (train.py:1242-1246): one pack kernel and
     two D2H copies instead of K*6 `.item()` syncs."""
-    n_keep = det["n_keep"].cpu()
-    if (n_keep < 0).any():
-        raise RuntimeError("NMS workspace overflow or class id out of range")
+    if bool((det["n_keep"] < 0).any()):  # graph algorithm overflowed for some image: dense re-run
+        nms_retry_overflow(det["boxes"], det["scores"], det["classes"], det["counts"], det["iou_threshold"],
+                           det["trick_max_numel"], det["keep"], det["n_keep"])
     rows, offsets = pack_detections(det)
     off = offsets.cpu().tolist()
     host = rows[:off[-1]].cpu().tolist()
