@@ -209,6 +209,42 @@ def test_loss_full_size_vs_oracle(yb):
         grad_close(p.grad, q.grad)
 
 
+def test_loss_two_rank_emulation_on_one_gpu(yb):
+    """SURVEY 8e on one GPU: two image shards, partial sums added as the all-reduce would, each
+    shard finalised with the global sums -> same losses and the same gradient rows as the
+    single-rank run over the whole batch."""
+    from yolo_from_scratch_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    B, nc = 6, 2
+    heads = [torch.randn(B, G, G, 3, 5 + nc, generator=g).cuda() for G in (16, 8, 4)]
+    rng = np.random.default_rng(5)
+    labels = []
+    for _ in range(B):
+        n = int(rng.integers(0, 9))
+        lab = np.zeros((n, 5))
+        lab[:, 0] = rng.integers(0, nc, n)
+        lab[:, 1:3] = rng.uniform(0.1, 0.9, (n, 2))
+        lab[:, 3:5] = rng.uniform(0.05, 0.6, (n, 2))
+        labels.append(lab)
+    tg = yb.build_targets(labels, ANCH, [16, 8, 4], nc, 128)
+    anc = [a.cuda() for a in ANCH]
+    w = ops.MULTISCALE_OBJ_WEIGHTS
+    full4, _, full_g = ops.loss_forward_backward(heads, tg, anc, nc, w, [True] * 3)
+    shards = [(0, 4), (4, 6)]  # unequal on purpose
+    cut = lambda ts, lo, hi: [t[lo:hi].contiguous() for t in ts]
+    parts = []
+    for lo, hi in shards:  # pass 1: every rank's partial sums
+        ops.loss_forward_backward(cut(heads, lo, hi), cut(tg, lo, hi), anc, nc, w, [True] * 3, b_global=B,
+                                  reduce_fn=lambda p: (parts.append(p.clone()), p)[1])
+    total = parts[0] + parts[1]
+    for lo, hi in shards:  # pass 2: finalise with the reduced sums
+        out4, _, grads = ops.loss_forward_backward(cut(heads, lo, hi), cut(tg, lo, hi), anc, nc, w, [True] * 3,
+                                                   b_global=B, reduce_fn=lambda p: total.clone())
+        close(out4, full4, rtol=2e-6, atol=1e-7)
+        for s in range(3):
+            close(grads[s], full_g[s][lo:hi], rtol=1e-5, atol=1e-9)
+
+
 # ---- target assignment ------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["a", "b", "c", "d", "e", "f", "g"])
 def test_build_targets_golden_bitexact(yb, golden, name):

@@ -1,0 +1,161 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, the ctypes structs match the C layout, the installer rebinds the reference's names,
+the launcher extracts the CLI block, and the product fails loudly without CUDA (no fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def yb():
+    import __graft_entry__ as g
+    g.build()
+    import yolo_from_scratch_b200 as m
+    return m
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "yolo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(yb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol(yb):
+    names = header_functions()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(yb._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/yolo_b200.h but not exported"
+    # and the binding table covers the header one to one
+    assert sorted(yb._lib.SIGNATURES) == names
+    assert yb._lib.lib().yb_version() >= 100
+
+
+def test_struct_layout_matches_c(yb, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "yolo_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+                   'sizeof(yb_loss_desc), offsetof(yb_loss_desc, pred), offsetof(yb_loss_desc, grad),'
+                   'sizeof(yb_heads_desc), offsetof(yb_heads_desc, pred));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    L, H = yb._lib.LossDesc, yb._lib.HeadsDesc
+    assert out == [ctypes.sizeof(L), L.pred.offset, L.grad.offset, ctypes.sizeof(H), H.pred.offset]
+
+
+def test_workspace_queries_do_not_need_a_gpu(yb):
+    lib = yb._lib.lib()
+    assert lib.yb_nms_workspace_bytes(64, 25200) >= lib.yb_nms_graph_workspace_bytes(64, 25200, 16)
+    assert lib.yb_nms_graph_workspace_bytes(64, 25200, 16) > lib.yb_nms_min_workspace_bytes(64, 25200)
+    d = yb._lib.LossDesc()
+    d.S, d.B, d.A, d.nc = 3, 64, 3, 1
+    for s, g in enumerate((80, 40, 20)):
+        d.H[s] = d.W[s] = g
+    assert lib.yb_loss_workspace_bytes(ctypes.byref(d)) >= 64 * 25200 * 4
+    assert lib.yb_ciou_scratch_bytes(10) >= 8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(yb):
+    x = torch.zeros(1, 4, 4, 3, 6)
+    a = torch.tensor([[10., 13.], [16., 30.], [33., 23.]])
+    for call in (lambda: yb.decode_predictions(x, a), lambda: yb.yolo_loss(x, x, a, 1),
+                 lambda: yb.batched_nms(torch.zeros(2, 4), torch.zeros(2), torch.zeros(2, dtype=torch.long), 0.5),
+                 lambda: yb.build_targets([[[0, .5, .5, .1, .1]]], [a, a, a], [8, 4, 2], 1, 64)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+
+
+def test_bad_arguments_are_reported(yb):
+    lib = yb._lib.lib()
+    rc = lib.yb_decode_fwd(None, None, None, 1, 4, 4, 3, 1, 640.0, None)
+    assert rc != 0 and b"null" in lib.yb_last_error()
+    rc = lib.yb_batched_nms(None, None, None, None, 1, 8, 0.5, 100000, 7, None, None, None, 0, None)
+    assert rc != 0
+
+
+def fake_train_module():
+    """A stand-in with the reference's hot-path names; internal callers resolve them through the
+    module globals exactly like train.py does."""
+    m = types.ModuleType("train")
+    src = '''
+class YOLODataset:
+    def compute_anchor_iou(self, box_wh, anchors): return "ref"
+    def __getitem__(self, idx): return "ref"
+def decode_predictions(raw_preds, anchors, img_size=640): return "ref"
+def ciou_loss(p, t, eps=1e-7): return "ref"
+def yolo_loss(predictions, targets, anchors, num_classes=1): return decode_predictions(predictions, anchors)
+def yolo_loss_multiscale(predictions, targets, anchors_list, num_classes=1): return "ref"
+def train_epoch(): return yolo_loss_multiscale
+def predict():
+    from torchvision.ops import batched_nms
+    return batched_nms
+if __name__ == "__main__":
+    RESULT = ("cli ran", decode_predictions.__module__)
+'''
+    exec(compile(src, "train.py", "exec"), m.__dict__)
+    return m, src
+
+
+def test_install_rebinds_reference_names(yb):
+    from yolo_from_scratch_b200 import install as inst, ops
+    m, _ = fake_train_module()
+    orig_getitem = m.YOLODataset.__getitem__
+    inst.install(m)
+    try:
+        assert m.decode_predictions is ops.decode_predictions and m.ciou_loss is ops.ciou_loss
+        assert m.yolo_loss is ops.yolo_loss and m.train_epoch() is ops.yolo_loss_multiscale
+        assert m.predict() is ops.batched_nms
+        assert m.YOLODataset.__getitem__ is not orig_getitem
+        inst.install(m)  # idempotent
+    finally:
+        inst.uninstall(m)
+    import torchvision
+    assert m.predict() is torchvision.ops.batched_nms and m.predict() is not ops.batched_nms
+    assert m.decode_predictions(None, None) == "ref" and m.YOLODataset.__getitem__ is orig_getitem
+
+
+def test_import_hook_and_launcher(yb, tmp_path):
+    from yolo_from_scratch_b200 import install as inst, ops, run
+    _, src = fake_train_module()
+    (tmp_path / "train.py").write_text(src)
+    sys.modules.pop("train", None)
+    old_path = list(sys.path)
+    try:
+        run.main([str(tmp_path / "train.py"), "data.yaml"])
+        mod = sys.modules["train"]
+        assert mod.decode_predictions is ops.decode_predictions      # patched at import
+        assert mod.RESULT == ("cli ran", ops.__name__)                # __main__ block ran in the patched namespace
+        assert sys.argv[1:] == ["data.yaml"]
+    finally:
+        inst.uninstall(sys.modules.get("train"))
+        inst.disable_import_hook()
+        sys.modules.pop("train", None)
+        sys.path[:] = old_path
+
+
+def test_install_on_live_reference(yb, reference_module):
+    """Build container only: the real reference module gets every hot-path name rebound."""
+    from yolo_from_scratch_b200 import install as inst, ops
+    ref = reference_module
+    assert inst.looks_like_reference(ref)
+    inst.install(ref)
+    try:
+        for n in inst.PATCHED_FUNCTIONS:
+            assert getattr(ref, n) is getattr(ops, n)
+        import inspect
+        for n in inst.PATCHED_FUNCTIONS:  # same parameter names and defaults as the reference
+            a = inspect.signature(ref.__yolo_b200_saved__[n])
+            b = inspect.signature(getattr(ops, n))
+            assert list(a.parameters) == list(b.parameters), n
+            assert [p.default for p in a.parameters.values()] == [p.default for p in b.parameters.values()], n
+    finally:
+        inst.uninstall(ref)

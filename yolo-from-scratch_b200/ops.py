@@ -50,6 +50,11 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def dist_global_batch(local_batch, group):
+    from .dist import global_batch
+    return global_batch(local_batch, group)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
@@ -203,7 +208,8 @@ def _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=No
     return d
 
 
-def loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want_grad, coef=None, group=None):
+def loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want_grad, coef=None, group=None, equal_shards=True,
+                          b_global=None, reduce_fn=None):
     """Run the fused kernels on device tensors.  Returns (out4, per_scale(S,3), grads list).
 
     `group`: optional torch.distributed process group; the batch is then a shard of a global
@@ -216,10 +222,15 @@ def loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want_grad, coef=No
         coef = [(BOX_WEIGHT, obj_weights[s], CLS_WEIGHT) for s in range(S)]
     grads = [torch.empty_like(p) if w else None for p, w in zip(preds, want_grad)]
     world = 1
-    if group is not None:
+    explicit = b_global
+    b_global = preds[0].shape[0]
+    if explicit is not None:
+        b_global = int(explicit)
+    elif group is not None:
         import torch.distributed as dist
         world = dist.get_world_size(group)
-    d = _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=preds[0].shape[0] * world)
+        b_global = b_global * world if equal_shards else dist_global_batch(preds[0].shape[0], group)
+    d = _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=b_global)
     ws_bytes = L.yb_loss_workspace_bytes(ctypes.byref(d))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     partials = torch.empty(S * 4, dtype=torch.float64, device=dev)
@@ -227,9 +238,11 @@ def loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want_grad, coef=No
     per_scale = torch.empty(S, 3, dtype=torch.float32, device=dev)
     st = _stream()
     _lib.check(L.yb_loss_partials(ctypes.byref(d), partials.data_ptr(), ws.data_ptr(), ws_bytes, st), "yb_loss_partials")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+    if reduce_fn is not None:
+        partials = reduce_fn(partials)          # test hook: emulate the collective on one GPU
+    elif world > 1:
+        from .dist import allreduce_partials
+        allreduce_partials(partials, group)
     _lib.check(L.yb_loss_finalize(ctypes.byref(d), partials.data_ptr(), out4.data_ptr(), per_scale.data_ptr(),
                                   ws.data_ptr(), ws_bytes, st), "yb_loss_finalize")
     return out4, per_scale, grads
