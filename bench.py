@@ -33,7 +33,6 @@ import torch  # noqa: E402
 
 IMG, NC, B_PER_GPU, MAX_GT = 640, 1, 64, 50
 CONF, IOU = 0.5, 0.4
-N_SETS = 4
 METRIC = "decode+global-NMS + CIoU-loss fwd+bwd throughput @640^2 bs64 nc1"
 UNIT = "images/s"
 
@@ -51,6 +50,8 @@ def parse():
     ap.add_argument("--iou", type=float, default=IOU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true")
     return ap.parse_args()
 
 
@@ -201,13 +202,13 @@ def reference_main(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, world, n_sets=4):
     return {
-        "workload": f"BASELINE configs[1]: nc={args.nc} heads at {args.img}x{args.img}, {args.batch} images/GPU, "
+        "workload": f"BASELINE {'configs[1]' if (args.nc, args.img, args.batch) == (1, 640, 64) else 'variant'}: nc={args.nc} heads at {args.img}x{args.img}, {args.batch} images/GPU, "
                     f"<= {MAX_GT} GT boxes/image, randn heads, conf {args.conf}, iou {args.iou}",
         "global_batch": args.batch * world, "images_per_gpu": args.batch, "img_size": args.img, "nc": args.nc,
         "conf_thres": args.conf, "iou_thres": args.iou, "parallelism": f"image-sharded x{world}",
-        "l2": f"inputs rotate over {N_SETS} sets per rank (working set > 126 MB L2)",
+        "l2": f"inputs rotate over {n_sets} sets per rank (working set > 126 MB L2)",
     }
 
 
@@ -216,7 +217,6 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 def b200_main(args, rank, local_rank, world):
     import yolo_from_scratch_b200 as yb
-    from yolo_from_scratch_b200 import ops
     lib = yb._lib.lib()  # raises if the CUDA extension is missing: no fallback
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (impl b200) needs a GPU; the CUDA path has no fallback")
@@ -227,23 +227,58 @@ def b200_main(args, rank, local_rank, world):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+    line = run_workload(args, rank, local_rank, world, dev, group, lib, full=True)
+    if rank == 0 and not args.no_other_configs and world == 1:
+        # the other single-GPU BASELINE configs, device-resident only, short runs (parity is in tests/)
+        import copy
+        others = {}
+        for name, (nc, img, batch, conf) in OTHER_CONFIGS.items():
+            a2 = copy.copy(args)
+            a2.nc, a2.img, a2.batch, a2.conf = nc, img, batch, conf
+            a2.steps, a2.warmup = max(3, min(args.steps, 6)), 3
+            try:
+                o = run_workload(a2, rank, local_rank, world, dev, group, lib, full=False)
+                others[name] = {k: o[k] for k in ("value", "ms_per_step", "loss_fwd_bwd_ms", "decode_nms_ms",
+                                                  "candidates_per_image", "kept_per_image", "kernels", "hbm_kernels",
+                                                  "roofline", "config")}
+            except Exception as e:  # pragma: no cover
+                others[name] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+        line["other_configs"] = others
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
+
+OTHER_CONFIGS = {  # BASELINE.json configs[2], configs[3]: (nc, img, images/GPU, conf)
+    "configs[2] nc80 640^2 B64 conf0.001": (80, 640, 64, 0.001),
+    "configs[3] nc80 1280^2 B32 conf0.001": (80, 1280, 32, 0.001),
+}
+
+
+def run_workload(args, rank, local_rank, world, dev, group, lib, full):
+    import yolo_from_scratch_b200 as yb
+    from yolo_from_scratch_b200 import ops
     B, img, nc = args.batch, args.img, args.nc
+    # rotate over enough input sets that the working set exceeds the 126 MB L2
+    T_est = sum(B * G * G * 3 for G in (img // 8, img // 16, img // 32)) * (5 + nc) * 4
+    n_sets = 4 if T_est * 3 * 4 <= (8 << 30) else 2
     grids = [img // 8, img // 16, img // 32]
     from oracle.ref_path import default_anchors  # constants only (train.py:372-374)
     anchors = [a.to(dev) for a in default_anchors()]
     weights = ops.MULTISCALE_OBJ_WEIGHTS
 
-    # N_SETS input sets per rank, on the device and mirrored in pinned host memory
+    # n_sets input sets per rank, on the device and (full run) mirrored in pinned host memory
     dev_sets, host_sets = [], []
-    for k in range(N_SETS):
+    for k in range(n_sets):
         seed = 1234 + 1000 * k + 100000 * rank
         heads = make_heads(B, img, nc, seed)
         labels = make_labels(np.random.default_rng(4321 + k + 1000 * rank), B, nc)
         tg = ops.build_targets(labels, anchors, grids, nc, img)
         d_heads = [h.to(dev) for h in heads]
         dev_sets.append((d_heads, tg))
-        host_sets.append(([h.pin_memory() for h in heads], [t.cpu().pin_memory() for t in tg]))
+        if full:
+            host_sets.append(([h.pin_memory() for h in heads], [t.cpu().pin_memory() for t in tg]))
+        del heads
     torch.cuda.synchronize()
     T_bytes = tensor_bytes(dev_sets[0][0])
     rows = sum(B * G * G * 3 for G in grids)
@@ -267,7 +302,7 @@ def b200_main(args, rank, local_rank, world):
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
     def step(i, conf=None, record=None):
-        heads, tg = dev_sets[i % N_SETS]
+        heads, tg = dev_sets[i % n_sets]
         if record:
             record[0].record()
         out4, per_scale, grads = ops.loss_forward_backward(heads, tg, anchors, nc, weights, [True] * 3, group=group)
@@ -282,14 +317,26 @@ def b200_main(args, rank, local_rank, world):
         step(i)
     barrier()
     # candidate statistics per input set (outside the timed region)
-    pair_counts, cand_counts, keep_counts = [], [], []
-    for k in range(N_SETS):
+    pair_counts, cand_counts, keep_counts, eval_counts, edge_counts = [], [], [], [], []
+    for k in range(n_sets):
         _, det = step(k)
         m = det["counts"].cpu().double()
         cand_counts.append(float(m.sum()))
-        pair_counts.append(float((m * (m - 1) / 2).sum()))
+        if nc > 1 and float(m.max()) * 4 > ops.TRICK_MAX_NUMEL_CUDA:
+            # per-class regime: only same-class pairs are algorithmic work
+            cl = det["classes"]
+            valid = torch.arange(cl.shape[1], device=dev)[None, :] < det["counts"][:, None]
+            oh = torch.zeros(B, nc, dtype=torch.float64, device=dev)
+            oh.scatter_add_(1, cl.clamp(0, nc - 1), valid.double())
+            pair_counts.append(float((oh * (oh - 1) / 2).sum()))
+        else:
+            pair_counts.append(float((m * (m - 1) / 2).sum()))
         keep_counts.append(float(det["n_keep"].cpu().double().sum()))
         assert int(det["n_keep"].min()) >= 0
+        st = ops.nms_graph_stats(det)
+        if st is not None:
+            eval_counts.append(st[0])
+            edge_counts.append(st[1])
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -323,6 +370,131 @@ def b200_main(args, rank, local_rank, world):
         k["share"] = k["ms_per_step"] / ksum if ksum else 0.0
 
     # ---- e2e through the public API with host buffers ---------------------------------------------
+    e2e = None
+    if full:
+        e2e = run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier,
+                      max_over_ranks)
+
+    # ---- variants: other confidence thresholds (device-resident, detect only) ---------------------
+    variants = {}
+    if full and not args.no_variants and rank == 0:
+        for conf in (0.25, 0.001):
+            for i in range(3):
+                step(i, conf=conf)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_it = max(5, args.steps // 3)
+            a.record()
+            for i in range(n_it):
+                heads, _ = dev_sets[i % n_sets]
+                det = ops.detect_batch(heads, anchors, img, nc, conf, args.iou)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / n_it
+            variants[f"conf_{conf}"] = {"decode_nms_ms": ms, "decode_nms_images_per_s": B / (ms * 1e-3),
+                                        "candidates_per_image": float(det["counts"].double().mean()),
+                                        "kept_per_image": float(det["n_keep"].double().mean())}
+    barrier()
+
+    if rank != 0:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(
+            f"nc{nc}_img{img}_B{B}", {})
+    except Exception:
+        pass
+    clocks = sampler.summary()
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+
+    # ---- HBM-bound kernels: algorithmic bytes / measured launch time --------------------
+    pos = float(np.mean([sum(float((t[..., 4] > 0.5).sum()) for t in tg) for _, tg in dev_sets]))
+    M_tot = float(np.mean(cand_counts))
+    sector = min(row_bytes, 32)
+    alg_bytes = {
+        # T (dense grad write) + obj sectors of pred and target + positive rows of pred and target
+        "loss_main_kernel": T_bytes + 2 * rows * sector + 2 * pos * row_bytes,
+        # objectness sector of every row
+        "filter_count_kernel": rows * sector,
+        # objectness sector of every row again + the candidate rows + 28 B of output per candidate
+        "filter_emit_kernel": rows * sector + M_tot * row_bytes + 28 * M_tot,
+    }
+    hbm_kernels = {}
+    for name, a_bytes in alg_bytes.items():
+        if name in kernels:
+            ach = a_bytes / (kernels[name]["avg_ms"] * 1e-3) / 1e9
+            hbm_kernels[name] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": ach / hbm_peak, "algorithmic_bytes": a_bytes, "share": kernels[name]["share"],
+                                 "traffic": traffic.get(name)}
+    # ---- NMS: pair throughput against the fp32 issue rate ---------------------------------------------
+    pairs = float(np.mean(pair_counts))
+    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / 17.0 / 1e9  # Gpair/s at 17 warp-instructions per 32 pairs
+    nms_ms = sum(kernels[k]["ms_per_step"] for k in kernels if k.startswith(("graph_", "nms_")))
+    nms_roof = {}
+    if "graph_edge_kernel" in kernels:
+        ek = kernels["graph_edge_kernel"]
+        evald = float(np.mean(eval_counts)) * 8.0 if eval_counts else None
+        nms_roof = {
+            "kernel": "graph_edge_kernel", "bound": "fp32-issue", "unit": "Gpair/s", "peak": issue_peak,
+            "peak_source": "148 SM x 4 schedulers x 32 lanes x sampled SM clock / 17 warp-instructions per 32 exact "
+                           "IoU>thr tests (SASS of the dense kernel)",
+            "algorithmic_pairs_per_launch": pairs,
+            "evaluated_pairs_per_launch": evald,
+            "edges_per_launch": float(np.mean(edge_counts)) if edge_counts else None,
+            # evaluated pair tests per second: how well the kernel uses the issue slots
+            "achieved": (evald / (ek["avg_ms"] * 1e-3) / 1e9) if evald else None,
+            "frac": (evald / (ek["avg_ms"] * 1e-3) / 1e9 / issue_peak) if evald else None,
+            # all pairs torchvision's kernel would evaluate, per second of the whole NMS (sort+edges+resolve)
+            "effective_algorithmic_gpairs": pairs / (nms_ms * 1e-3) / 1e9 if nms_ms else None,
+            "share": ek["share"], "traffic": traffic.get("graph_edge_kernel"),
+        }
+    dominant = max(kernels, key=lambda k: kernels[k]["share"]) if kernels else None
+    if dominant in hbm_kernels:
+        roofline = dict(hbm_kernels[dominant], kernel=dominant, peak_source=peak_src)
+    elif dominant == "graph_edge_kernel":
+        roofline = dict(nms_roof)
+        roofline["note"] = ("dominant kernel is the NMS edge discovery: SIMT fp32 compare/min/max work, no HBM or "
+                            "tensor bound applies (north_star: IoU pair-throughput for NMS); HBM-bound kernels are "
+                            "under hbm_kernels")
+    else:
+        roofline = {"kernel": dominant, "bound": "latency", "achieved": None, "peak": None, "frac": None,
+                    "share": kernels[dominant]["share"] if dominant else None}
+    for v in hbm_kernels.values():
+        v["peak_source"] = peak_src
+
+    cpu_baseline = torch_gpu = None
+    if full and world == 1 and not args.no_cpu_baseline:
+        v, ms, cores, sample = run_cpu_reference(args, min(B, 8), 2, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
+    if full and world == 1 and not args.no_torch_gpu_baseline:
+        torch_gpu = run_torch_gpu_reference(args, dev, min(B, 8))
+
+    line = {
+        "metric": METRIC, "value": B * world / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world, n_sets),
+        "loss_fwd_bwd_ms": loss_ms, "decode_nms_ms": det_ms, "decode_nms_images_per_s": B * world / (det_ms * 1e-3),
+        "candidates_per_image": float(np.mean(cand_counts)) / B, "kept_per_image": float(np.mean(keep_counts)) / B,
+        "e2e": e2e, "gpu_launches": int(launches), "kernels": kernels,
+        "roofline": roofline, "hbm_kernels": hbm_kernels, "roofline_nms": nms_roof, "cpu_baseline": cpu_baseline,
+        "torch_gpu_baseline": torch_gpu, "clocks": clocks, "variants": variants,
+    }
+    del dev_sets, host_sets
+    return line
+
+
+def run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier, max_over_ranks):
+    """Same step through the public API with pinned HOST buffers: H2D of heads + dense targets, loss
+    fwd+bwd, detect, pack, D2H of the 4 losses and the detection rows — all inside the timed region."""
+    B, img, nc = args.batch, args.img, args.nc
     loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
     off_host = torch.empty(B + 1, dtype=torch.int32).pin_memory()
     det_host = torch.empty(B * sum(G * G * 3 for G in grids), 6, dtype=torch.float32).pin_memory()
@@ -330,7 +502,7 @@ def b200_main(args, rank, local_rank, world):
     d2h_acc = []
 
     def e2e_step(i):
-        h_heads, h_tg = host_sets[i % N_SETS]
+        h_heads, h_tg = host_sets[i % n_sets]
         preds = [h.to(dev, non_blocking=True).requires_grad_(True) for h in h_heads]
         tgts = [t.to(dev, non_blocking=True) for t in h_tg]
         if group is None:
@@ -361,83 +533,56 @@ def b200_main(args, rank, local_rank, world):
     g1.record()
     barrier()
     e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)) / args.steps
-    e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(np.mean(d2h_acc)),
-           "api": "yolo_loss_multiscale(...).backward() + detect_batch + pack_detections, pinned host tensors"}
+    return {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(np.mean(d2h_acc)),
+            "api": "yolo_loss_multiscale(...).backward() + detect_batch + pack_detections, pinned host tensors"}
 
-    # ---- variants: other confidence thresholds (device-resident, detect only) ---------------------
-    variants = {}
-    if not args.no_variants and rank == 0:
-        for conf in (0.25, 0.001):
-            for i in range(3):
-                step(i, conf=conf)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_it = max(5, args.steps // 3)
-            cands = 0.0
-            a.record()
-            for i in range(n_it):
-                heads, _ = dev_sets[i % N_SETS]
-                det = ops.detect_batch(heads, anchors, img, nc, conf, args.iou)
-            b.record()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / n_it
-            cands = float(det["counts"].double().mean())
-            variants[f"conf_{conf}"] = {"decode_nms_ms": ms, "decode_nms_images_per_s": B / (ms * 1e-3),
-                                        "candidates_per_image": cands,
-                                        "kept_per_image": float(det["n_keep"].double().mean())}
-    barrier()
 
-    if rank != 0:
-        return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
-    except Exception:
-        pass
-    # loss_main_kernel: A_loss = T (grad write) + 2*rows*min(row,32) (obj sectors) + 2*P*row
-    pos = float(np.mean([sum(float((t[..., 4] > 0.5).sum()) for t in tg) for _, tg in dev_sets]))
-    a_loss = T_bytes + 2 * rows * min(row_bytes, 32) + 2 * pos * row_bytes
-    lm = kernels.get("loss_main_kernel", {"avg_ms": float("nan")})
-    achieved = a_loss / (lm["avg_ms"] * 1e-3) / 1e9
-    roofline = {"kernel": "loss_main_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "peak_source": peak_src, "algorithmic_bytes": a_loss,
-                "traffic": traffic.get("loss_main_kernel")}
-    mk = kernels.get("nms_mask_kernel", {"avg_ms": float("nan")})
-    pairs = float(np.mean(pair_counts))
-    clocks = sampler.summary()
-    sm_mhz = clocks.get("sm_mhz") or 1965.0
-    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / 17.0 / 1e9  # Gpair/s at 17 warp-instructions per 32 pairs
-    roofline_nms = {"kernel": "nms_mask_kernel", "bound": "fp32-issue", "pairs_per_launch": pairs,
-                    "achieved": pairs / (mk["avg_ms"] * 1e-3) / 1e9, "unit": "Gpair/s", "peak": issue_peak,
-                    "frac": pairs / (mk["avg_ms"] * 1e-3) / 1e9 / issue_peak,
-                    "peak_source": "148 SM x 4 issue slots x 32 lanes x sampled SM clock / 17 instructions per pair (SASS)",
-                    "traffic": traffic.get("nms_mask_kernel")}
+def run_torch_gpu_reference(args, dev, sample_images):
+    """The reference's GPU-PyTorch path (north_star's comparison point): the oracle port of train.py's
+    loss (:840-886, autograd backward) and of predict()'s per-image decode/filter + torchvision's CUDA
+    batched_nms (:1152-1238), run on CUDA tensors.  Reported only; not on the product path."""
+    from oracle import ref_path as R
+    import torchvision
+    B, img, nc = args.batch, args.img, args.nc
+    anchors = [a.to(dev) for a in R.default_anchors()]
+    heads = [h.to(dev) for h in make_heads(B, img, nc, 1234)]
+    labels = make_labels(np.random.default_rng(4321), B, nc)
+    grids = [img // 8, img // 16, img // 32]
+    tg = [R.assign_targets(l, R.default_anchors(), grids, nc, img) for l in labels]
+    tgts = [torch.from_numpy(np.stack([t[s] for t in tg])).to(dev) for s in range(3)]
 
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        v, ms, cores, sample = run_cpu_reference(args, min(B, 8), 2, 1)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
+    def loss_step():
+        preds = [h.clone().requires_grad_(True) for h in heads]
+        R.multiscale_loss(preds, tgts, anchors, nc)[0].backward()
 
-    line = {
-        "metric": METRIC, "value": B * world / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, world),
-        "loss_fwd_bwd_ms": loss_ms, "decode_nms_ms": det_ms, "decode_nms_images_per_s": B * world / (det_ms * 1e-3),
-        "candidates_per_image": float(np.mean(cand_counts)) / B, "kept_per_image": float(np.mean(keep_counts)) / B,
-        "e2e": e2e, "gpu_launches": int(launches), "kernels": kernels,
-        "roofline": roofline, "roofline_nms": roofline_nms, "cpu_baseline": cpu_baseline, "clocks": clocks,
-        "variants": variants,
-    }
-    print(json.dumps(line), flush=True)
+    def det_step(n_img):
+        kept = 0
+        for b in range(n_img):  # predict() is single-image: a batch is a python loop (SURVEY 3c)
+            bx, sc, cl = R.candidates([h[b:b + 1] for h in heads], anchors, img, nc, args.conf)
+            if bx.shape[0]:
+                kept += int(torchvision.ops.batched_nms(bx, sc, cl.to(dev), args.iou).numel())
+        return kept
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3) / n
+
+    loss_ms = timed(loss_step, 5)                       # whole batch of B images
+    det_ms = timed(lambda: det_step(sample_images), 3)  # sample_images images
+    per_image_ms = loss_ms / B + det_ms / sample_images
+    return {"value": 1e3 / per_image_ms, "unit": UNIT, "loss_fwd_bwd_ms": loss_ms,
+            "decode_nms_ms_per_image": det_ms / sample_images, "kind": "port on CUDA tensors (torch eager + "
+            "torchvision CUDA nms)", "sample": f"loss on all {B} images, decode+NMS on {sample_images} of {B} images"}
 
 
 def main():

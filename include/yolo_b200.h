@@ -199,6 +199,12 @@ int yb_batched_nms(const float* boxes, const float* scores, const int64_t* class
                    long long trick_max_numel, int algo, int64_t* keep, int* n_keep,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* Statistics of the last YB_NMS_GRAPH call that used workspace `ws` (bench/tests; synchronises the
+ * stream): pair-test evaluations in units of 8 pairs (one row against an 8-column sub-tile) and edges
+ * found, summed over the B images.  Outputs are HOST pointers (nullable). */
+int yb_nms_graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned long long* evals_host,
+                       unsigned long long* edges_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * detection list of predict()                                              train.py:1236-1246
  *   Packs the kept detections of a batch as rows (x1, y1, x2, y2, conf, class) fp32, image after

@@ -170,7 +170,7 @@ def candidates(preds, anchors_list, img_size, num_classes=1, conf=0.5, scale=1.0
             continue
         if num_classes == 1:                                                  # :1184-1189
             prob = rows[:, 5]
-            cid = torch.zeros(rows.shape[0], dtype=torch.long)
+            cid = torch.zeros(rows.shape[0], dtype=torch.long, device=rows.device)
         else:
             prob, cid = rows[:, 5:].max(dim=1)
         cx, cy, w, h = (rows[:, k] * img_size for k in range(4))              # :1192-1195

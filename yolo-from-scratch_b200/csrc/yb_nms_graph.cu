@@ -24,10 +24,14 @@
 // Bound: fp32 SIMT issue on the pair evaluations that survive culling.
 #include "yb_common.cuh"
 #include "yb_sort.cuh"
+#include <vector>
 
 namespace yb {
 
 constexpr int kTile = 32;
+constexpr int kSub = 8;             // columns per sub-tile (row culling granularity)
+constexpr int kSubs = kTile / kSub;
+constexpr int kGatherThreads = 256;
 constexpr int kEdgeThreads = 256;
 constexpr int kResolveThreads = 1024;
 
@@ -38,6 +42,7 @@ struct GImg {
     int n_tiles;
     u32 n_edges;
     float s_off, t2;  // coordinate offset step; pruning threshold thr*(1-2^-10) (or -1: no pruning)
+    unsigned long long n_evals;  // statistics: row-vs-8-columns evaluations (8 pair tests each)
 };
 
 struct GArgs {
@@ -49,11 +54,15 @@ struct GArgs {
     float thr;
     int thr_fast_ok;
     long long trick_max_numel;
-    u32 *k0, *v0, *k1, *v1, *k2, *v2;  // (B,cap); v0[r] = original index of score rank r
+    u32 *k0, *v0, *k1, *v1, *k2, *v2;  // (B,cap) radix ping-pong buffers
+    u32* order;                        // (B,cap) score rank -> original index      (score CTA)
+    u32* rinv;                         // (B,cap) original index -> score rank      (score CTA)
+    u32* pos;                          // (B,cap) position -> original index        (spatial CTA)
     float4* sboxes;                    // (B,cap) boxes in position order (offset applied)
     u32* srank;                        // (B,cap) position -> score rank
     u32* scls;                         // (B,cap) position -> class id (per-class mode)
     float4* tstat;                     // (B,tcap,2) tile bbox | {amin, amax, cmin, cmax}
+    float4* sstat;                     // (B,tcap,kSubs,2) sub-tile bbox | {amin, amax, -, -}
     GImg* info;
     u32* ticket;
     uint2* edges;
@@ -83,6 +92,9 @@ __device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// sort: two independent CTAs per image (blockIdx.y = 0: score order, 1: spatial order)
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSortThreads) graph_sort_kernel(const GArgs a) {
     __shared__ u32 s_hist[32 * 256];
     __shared__ u32 s_tot[256];
@@ -96,19 +108,36 @@ __global__ void __launch_bounds__(kSortThreads) graph_sort_kernel(const GArgs a)
     int M = a.counts ? a.counts[b] : a.cap;
     M = M < 0 ? 0 : (M > a.cap ? a.cap : M);
     GImg* info = a.info + b;
+    if (b == 0 && blockIdx.y == 0 && tid == 0) *a.ticket = 0u;
     if (M == 0) {
-        if (tid == 0) {
-            GImg z = {0, G_PLAIN, 0, 0, 0, 0u, 0.0f, -1.0f};
+        if (tid == 0 && blockIdx.y == 1) {
+            GImg z = {0, G_PLAIN, 0, 0, 0, 0u, 0.0f, -1.0f, 0ull};
             *info = z;
         }
         return;
     }
     const float4* boxes = a.boxes + off;
-    const float* scores = a.scores + off;
     const int64_t* classes = a.classes ? a.classes + off : nullptr;
-    const int mode = !classes ? G_PLAIN : ((long long)M * 4 <= a.trick_max_numel ? G_TRICK : G_CLASS);
 
-    // ---- reductions ---------------------------------------------------------------------------
+    if (blockIdx.y == 0) {
+        // ---- stable descending score sort: order[r] = original index, rinv[index] = r ---------------
+        const float* scores = a.scores + off;
+        u32 *ka = a.k0 + off, *va = a.v0 + off, *kb = a.k1 + off, *vb = a.v1 + off;
+        for (int i = tid; i < M; i += kSortThreads) { ka[i] = desc_key(scores[i]); va[i] = (u32)i; }
+        __syncthreads();
+        radix_sort(ka, va, kb, vb, M, 0, 32, s_hist, s_tot, &s_skip);
+        u32* order = a.order + off;
+        u32* rinv = a.rinv + off;
+        for (int r = tid; r < M; r += kSortThreads) {
+            const u32 idx = va[r];
+            order[r] = idx;
+            rinv[idx] = (u32)r;
+        }
+        return;
+    }
+
+    // ---- reductions (torchvision's boxes.max(), validity, centre range, class range) ------------------
+    const int mode = !classes ? G_PLAIN : ((long long)M * 4 <= a.trick_max_numel ? G_TRICK : G_CLASS);
     float mx = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
     int bad = 0, maxcls = 0;
     for (int i = tid; i < M; i += kSortThreads) {
@@ -139,106 +168,101 @@ __global__ void __launch_bounds__(kSortThreads) graph_sort_kernel(const GArgs a)
     if (mode == G_TRICK && !((float)maxcls * s_off + fabsf(mx) <= 1e17f)) bad |= 1;
     const bool exact = (bad & 1) || !a.thr_fast_ok;
 
-    // ---- stable descending score sort: v0[r] = original index ------------------------------------
-    u32 *k0 = a.k0 + off, *v0 = a.v0 + off, *k1 = a.k1 + off, *v1 = a.v1 + off;
-    u32 *k2 = a.k2 + off, *v2 = a.v2 + off;
-    for (int i = tid; i < M; i += kSortThreads) { k0[i] = desc_key(scores[i]); v0[i] = (u32)i; }
-    __syncthreads();
-    {
-        u32 *ka = k0, *va = v0, *kb = k1, *vb = v1;
-        radix_sort(ka, va, kb, vb, M, 0, 32, s_hist, s_tot, &s_skip);
-        if (va != v0) {
-            for (int i = tid; i < M; i += kSortThreads) v0[i] = va[i];
-            __syncthreads();
-        }
-    }
-
-    // ---- spatial order: (class | area octave pair | Morton(centre)) ---------------------------------
+    // ---- spatial order: (class | area octave pair | Morton(centre)), stable by original index --------
+    u32 *ka = a.k2 + off, *va = a.v2 + off, *kb = a.srank + off, *vb = a.scls + off;  // scratch until the gather
     const float qs = (cmax > cmin) ? 255.0f / (cmax - cmin) : 0.0f;
-    for (int r = tid; r < M; r += kSortThreads) {
-        const u32 idx = v0[r];
-        const float4 q = boxes[idx];
+    for (int i = tid; i < M; i += kSortThreads) {
+        const float4 q = boxes[i];
         const float area = (q.z - q.x) * (q.w - q.y);
         const u32 bucket = (__float_as_uint(area) >> 24) & 0x7fu;
         const float fx = fminf(fmaxf(((q.x + q.z) * 0.5f - cmin) * qs, 0.0f), 255.0f);
         const float fy = fminf(fmaxf(((q.y + q.w) * 0.5f - cmin) * qs, 0.0f), 255.0f);
         const u32 mort = spread8((u32)fx) | (spread8((u32)fy) << 1);
-        const u32 c = classes ? ((u32)classes[idx] & 0x1ffu) : 0u;
-        k1[r] = (c << 23) | (bucket << 16) | mort;
-        v1[r] = (u32)r;
+        const u32 c = classes ? ((u32)classes[i] & 0x1ffu) : 0u;
+        ka[i] = (c << 23) | (bucket << 16) | mort;
+        va[i] = (u32)i;
     }
     __syncthreads();
-    u32 *ka = k1, *va = v1, *kb = k2, *vb = v2;
     radix_sort(ka, va, kb, vb, M, 0, 32, s_hist, s_tot, &s_skip);
-
-    // ---- gather in position order; coordinate-offset trick (boxes.py:99-101) -------------------------
-    float4* sb = a.sboxes + off;
-    u32* srank = a.srank + off;
-    u32* scls = a.scls + off;
-    for (int p = tid; p < M; p += kSortThreads) {
-        const u32 r = va[p];
-        const u32 idx = v0[r];
-        float4 q = boxes[idx];
-        u32 c = 0;
-        if (classes) c = (u32)classes[idx];
-        if (mode == G_TRICK) {
-            const float o = (float)classes[idx] * s_off;
-            q.x += o; q.y += o; q.z += o; q.w += o;
-        }
-        sb[p] = q;
-        srank[p] = r;
-        scls[p] = (mode == G_CLASS) ? c : 0u;
-    }
-    __syncthreads();
-
-    // ---- tile statistics -----------------------------------------------------------------------------
-    const int n_tiles = (M + kTile - 1) / kTile;
-    float4* ts = a.tstat + (size_t)b * a.tcap * 2;
-    for (int t = warp; t < n_tiles; t += kSortThreads / 32) {
-        const int p = t * kTile + lane;
-        float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY, amin = INFINITY, amax = -INFINITY;
-        u32 c0 = 0xffffffffu, c1 = 0u;
-        if (p < M) {
-            const float4 q = sb[p];
-            x1 = q.x; y1 = q.y; x2 = q.z; y2 = q.w;
-            amin = amax = (q.z - q.x) * (q.w - q.y);
-            c0 = c1 = scls[p];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-            y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-            x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o));
-            y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
-            amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-            c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
-            c1 = max(c1, __shfl_xor_sync(0xffffffffu, c1, o));
-        }
-        if (lane == 0) {
-            ts[t * 2 + 0] = make_float4(x1, y1, x2, y2);
-            ts[t * 2 + 1] = make_float4(amin, amax, __uint_as_float(c0), __uint_as_float(c1));
-        }
-    }
+    u32* pos = a.pos + off;
+    for (int p = tid; p < M; p += kSortThreads) pos[p] = va[p];
     if (tid == 0) {
         GImg o;
         o.M = M; o.mode = mode; o.exact = exact ? 1 : 0;
         o.overflow = (bad & 2) ? 2 : 0;
-        o.n_tiles = n_tiles; o.n_edges = 0u; o.s_off = s_off;
+        o.n_tiles = (M + kTile - 1) / kTile; o.n_edges = 0u; o.s_off = s_off;
         o.t2 = exact ? -1.0f : a.thr * (1.0f - 9.765625e-4f);
+        o.n_evals = 0ull;
         *info = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather in position order (coordinate-offset trick, boxes.py:99-101) + tile / sub-tile statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArgs a) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GImg info = a.info[b];
+    const int t = blockIdx.x * (kGatherThreads / 32) + warp;
+    if (t >= info.n_tiles) return;
+    const int M = info.M;
+    const size_t off = (size_t)b * a.cap;
+    const float4* boxes = a.boxes + off;
+    const int64_t* classes = a.classes ? a.classes + off : nullptr;
+    const int p = t * kTile + lane;
+    float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY, amin = INFINITY, amax = -INFINITY;
+    u32 c0 = 0xffffffffu, c1 = 0u;
+    if (p < M) {
+        const u32 idx = a.pos[off + p];
+        float4 q = boxes[idx];
+        u32 c = 0;
+        if (classes) c = (u32)classes[idx];
+        if (info.mode == G_TRICK) {
+            const float o = (float)classes[idx] * info.s_off;
+            q.x += o; q.y += o; q.z += o; q.w += o;
+        }
+        const u32 cls = (info.mode == G_CLASS) ? c : 0u;
+        a.sboxes[off + p] = q;
+        a.srank[off + p] = a.rinv[off + idx];
+        a.scls[off + p] = cls;
+        x1 = q.x; y1 = q.y; x2 = q.z; y2 = q.w;
+        amin = amax = (q.z - q.x) * (q.w - q.y);
+        c0 = c1 = cls;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o));
+        y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+        amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
+        c1 = max(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+        if (o == kSub / 2 && (lane & (kSub - 1)) == 0) {  // statistics of this lane's 8-box sub-tile
+            float4* ss = a.sstat + (((size_t)b * a.tcap + t) * kSubs + (lane / kSub)) * 2;
+            ss[0] = make_float4(x1, y1, x2, y2);
+            ss[1] = make_float4(amin, amax, 0.0f, 0.0f);
+        }
+    }
+    if (lane == 0) {
+        float4* ts = a.tstat + ((size_t)b * a.tcap + t) * 2;
+        ts[0] = make_float4(x1, y1, x2, y2);
+        ts[1] = make_float4(amin, amax, __uint_as_float(c0), __uint_as_float(c1));
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // edge discovery
 // ------------------------------------------------------------------------------------------------
-struct RowAux { float area; u32 rank; u32 cls; u32 pad; };
+struct RowAux { u32 rank; u32 cls; };
 
 __global__ void __launch_bounds__(kEdgeThreads) graph_edge_kernel(const GArgs a) {
     __shared__ float4 s_row[kEdgeThreads / 32][kTile];
+    __shared__ float s_area[kEdgeThreads / 32][kTile];
     __shared__ RowAux s_aux[kEdgeThreads / 32][kTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / kSub;  // this lane's column sub-tile
     const unsigned lt_mask = (1u << lane) - 1u;
     const u32 total = (u32)a.tcap * (u32)a.B;
     const float kEps = 9.5367431640625e-07f;     // 2^-20
@@ -259,10 +283,12 @@ __global__ void __launch_bounds__(kEdgeThreads) graph_edge_kernel(const GArgs a)
         const u32* srank = a.srank + off;
         const u32* scls = a.scls + off;
         const float4* ts = a.tstat + (size_t)b * a.tcap * 2;
+        const float4* ss = a.sstat + (size_t)b * a.tcap * kSubs * 2;
         uint2* edges = a.edges + (u64)b * a.edges_per_img;
         const bool prune = info.t2 >= 0.0f;
         const float t2 = info.t2;
         const bool class_mode = info.mode == G_CLASS;
+        const bool all_exact = info.exact != 0;
 
         // this lane's row of tile I
         const int rp = I * kTile + lane;
@@ -272,12 +298,15 @@ __global__ void __launch_bounds__(kEdgeThreads) graph_edge_kernel(const GArgs a)
         if (rvalid) { rq = sb[rp]; rrank = srank[rp]; rcls = scls[rp]; }
         const float rw = rq.z - rq.x, rh = rq.w - rq.y;
         const float rS = rw * rh;
+        const float rw_t = t2 * rw, rh_t = t2 * rh, rS_t = t2 * rS;
         __syncwarp();
         s_row[warp][lane] = rq;
-        s_aux[warp][lane] = RowAux{rS, rrank, rcls, 0u};
+        s_area[warp][lane] = rS;
+        s_aux[warp][lane] = RowAux{rrank, rcls};
         __syncwarp();
         const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
         const u32 icmax = __float_as_uint(ia.w);
+        u32 n_evals = 0;
 
         for (int J0 = I; J0 < info.n_tiles; J0 += 32) {
             const int Jl = J0 + lane;
@@ -299,56 +328,61 @@ __global__ void __launch_bounds__(kEdgeThreads) graph_edge_kernel(const GArgs a)
                 const int jl = __ffs(cand) - 1;
                 cand &= cand - 1u;
                 const int J = J0 + jl;
-                // tile J statistics, broadcast from the lane that tested it
-                const float jx1 = __shfl_sync(0xffffffffu, jb.x, jl), jy1 = __shfl_sync(0xffffffffu, jb.y, jl);
-                const float jx2 = __shfl_sync(0xffffffffu, jb.z, jl), jy2 = __shfl_sync(0xffffffffu, jb.w, jl);
-                const float jamin = __shfl_sync(0xffffffffu, ja.x, jl), jamax = __shfl_sync(0xffffffffu, ja.y, jl);
                 // this lane's column of tile J
                 const int cp = J * kTile + lane;
                 const bool cvalid = cp < M;
                 float4 cq = make_float4(far, far, far, far);
-                u32 crank = 0xffffffffu, ccls = 0u;
-                if (cvalid) { cq = sb[cp]; crank = srank[cp]; ccls = scls[cp]; }
+                if (cvalid) cq = sb[cp];
                 const float cw = cq.z - cq.x, ch = cq.w - cq.y;
-                const float cS = cw * ch;
-                // row culling: lane <-> row of tile I against the bounding box of tile J
-                bool rok = rvalid;
-                if (prune) {
-                    const float ox = fminf(rq.z, jx2) - fmaxf(rq.x, jx1);
-                    const float oy = fminf(rq.w, jy2) - fmaxf(rq.y, jy1);
-                    rok = rok && ox > 0.0f && oy > 0.0f && ox >= t2 * rw && oy >= t2 * rh && jamax >= t2 * rS &&
-                          rS >= t2 * jamin;
+                // row culling: lane <-> row of tile I against the statistics of each 8-column sub-tile of J;
+                // this lane keeps the queue of rows that survive against ITS sub-tile
+                unsigned q = 0u;
+#pragma unroll
+                for (int s = 0; s < kSubs; ++s) {
+                    bool rok = rvalid;
+                    if (prune) {
+                        const float4 sbx = ss[(J * kSubs + s) * 2], sar = ss[(J * kSubs + s) * 2 + 1];
+                        const float ox = fminf(rq.z, sbx.z) - fmaxf(rq.x, sbx.x);
+                        const float oy = fminf(rq.w, sbx.w) - fmaxf(rq.y, sbx.y);
+                        rok = rok && ox > 0.0f && oy > 0.0f && ox >= rw_t && oy >= rh_t && sar.y >= rS_t &&
+                              rS >= t2 * sar.x;
+                    } else {
+                        rok = rok && (J * kTile + s * kSub) < M;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, rok);
+                    n_evals += __popc(m);
+                    if (s == grp) q = m;
                 }
-                unsigned rows = __ballot_sync(0xffffffffu, rok);
-                while (rows) {
-                    const int i = __ffs(rows) - 1;
-                    rows &= rows - 1u;
+                while (__any_sync(0xffffffffu, q != 0u)) {
+                    const bool act = q != 0u;
+                    const int i = act ? (__ffs(q) - 1) : 0;
+                    q &= q - 1u;
                     const float4 r = s_row[warp][i];
-                    const RowAux ra = s_aux[warp][i];
+                    const float rarea = s_area[warp][i];
                     const float left = fmaxf(r.x, cq.x), right = fminf(r.z, cq.z);
                     const float top = fmaxf(r.y, cq.y), bottom = fminf(r.w, cq.w);
                     const float w = fmaxf(right - left, 0.0f), h = fmaxf(bottom - top, 0.0f);
                     const float inter = w * h;
-                    bool pr, need_exact = info.exact != 0;
-                    if (!need_exact) {
-                        // row taken as `a`; the true roles change den by <= 2 ulp, inside the margin
-                        const float den = __fmaf_rn(cw, ch, ra.area) - inter;
-                        const float tt = a.thr * den;
-                        const float d = inter - tt;
-                        pr = d > 0.0f;
-                        need_exact = !(fabsf(d) > __fmaf_rn(tt, kEps, kTiny));
-                    }
-                    if (need_exact) {
+                    // row taken as `a`; the true roles change den by <= 2 ulp, inside the margin
+                    const float den0 = __fmaf_rn(cw, ch, rarea) - inter;
+                    const float tt = a.thr * den0;
+                    const float d = inter - tt;
+                    bool pr = act && d > 0.0f;
+                    const bool amb = act && (all_exact || !(fabsf(d) > __fmaf_rn(tt, kEps, kTiny)));
+                    if (!__any_sync(0xffffffffu, pr || amb)) continue;
+                    // rare: a candidate edge.  Exact arithmetic where needed, validity, same class, dedup.
+                    const RowAux ra = s_aux[warp][i];
+                    u32 crank = 0xffffffffu, ccls = 0u;
+                    if (cvalid) { crank = srank[cp]; ccls = scls[cp]; }
+                    if (amb) {
                         // torchvision devIoU with a = the higher-scored box
                         const bool row_a = ra.rank < crank;
-                        const float sa = row_a ? ra.area : cS;
+                        const float sa = row_a ? rarea : cw * ch;
                         const float bw = row_a ? cw : (r.z - r.x), bh = row_a ? ch : (r.w - r.y);
                         const float den = __fmaf_rn(bw, bh, sa) - inter;
                         pr = (inter / den) > a.thr;
                     }
-                    if (__ballot_sync(0xffffffffu, pr) == 0u) continue;
-                    // rare: an edge.  Validity, same class (per-class mode), each unordered pair once.
-                    bool fin = pr && cvalid && (!class_mode || ccls == ra.cls) && (J != I || lane > i);
+                    const bool fin = pr && cvalid && (!class_mode || ccls == ra.cls) && (J != I || lane > i);
                     const unsigned em = __ballot_sync(0xffffffffu, fin);
                     if (em) {
                         const int leader = __ffs(em) - 1;
@@ -363,6 +397,7 @@ __global__ void __launch_bounds__(kEdgeThreads) graph_edge_kernel(const GArgs a)
                 }
             }
         }
+        if (lane == 0 && n_evals) atomicAdd(&a.info[b].n_evals, (unsigned long long)n_evals);
     }
 }
 
@@ -419,7 +454,7 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
         if (!__syncthreads_or(left)) break;
     }
     // ---- emit kept indices in descending score order (K is indexed by score rank) ----
-    const u32* order = a.v0 + (size_t)b * a.cap;
+    const u32* order = a.order + (size_t)b * a.cap;
     const int chunk = (nw + kResolveThreads - 1) / kResolveThreads;
     const int c0 = min(tid * chunk, nw), c1 = min(c0 + chunk, nw);
     u32 sum = 0;
@@ -451,7 +486,7 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
 
 // ---- host side -------------------------------------------------------------------------------
 struct GLayout {
-    size_t k[6], sboxes, srank, scls, tstat, info, ticket, edges, total;
+    size_t k[6], order, rinv, pos, sboxes, srank, scls, tstat, sstat, info, ticket, edges, total;
 };
 
 static inline size_t g_align(size_t x) { return (x + 255) / 256 * 256; }
@@ -462,10 +497,14 @@ static GLayout graph_layout(int B, int cap) {
     const size_t n = (size_t)B * cap;
     const size_t tcap = ((size_t)cap + kTile - 1) / kTile;
     for (int i = 0; i < 6; ++i) { L.k[i] = o; o = g_align(o + n * 4); }
+    L.order = o; o = g_align(o + n * 4);
+    L.rinv = o; o = g_align(o + n * 4);
+    L.pos = o; o = g_align(o + n * 4);
     L.sboxes = o; o = g_align(o + n * 16);
     L.srank = o; o = g_align(o + n * 4);
     L.scls = o; o = g_align(o + n * 4);
     L.tstat = o; o = g_align(o + (size_t)B * tcap * 32);
+    L.sstat = o; o = g_align(o + (size_t)B * tcap * kSubs * 32);
     L.info = o; o = g_align(o + (size_t)B * sizeof(GImg));
     L.ticket = o; o = g_align(o + 256);
     L.edges = o;
@@ -490,16 +529,19 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     a.trick_max_numel = trick_max_numel;
     a.k0 = (u32*)(w + L.k[0]); a.v0 = (u32*)(w + L.k[1]); a.k1 = (u32*)(w + L.k[2]);
     a.v1 = (u32*)(w + L.k[3]); a.k2 = (u32*)(w + L.k[4]); a.v2 = (u32*)(w + L.k[5]);
+    a.order = (u32*)(w + L.order); a.rinv = (u32*)(w + L.rinv); a.pos = (u32*)(w + L.pos);
     a.sboxes = (float4*)(w + L.sboxes); a.srank = (u32*)(w + L.srank); a.scls = (u32*)(w + L.scls);
     a.tstat = (float4*)(w + L.tstat);
+    a.sstat = (float4*)(w + L.sstat);
     a.info = (GImg*)(w + L.info);
     a.ticket = (u32*)(w + L.ticket);
     a.edges = (uint2*)(w + L.edges);
     a.edges_per_img = (ws_bytes - L.edges) / 8 / (size_t)B;
     a.keep = keep; a.n_keep = n_keep;
 
-    YB_CUDA(cudaMemsetAsync(a.ticket, 0, 256, st));
-    YB_LAUNCH("graph_sort_kernel", st, graph_sort_kernel<<<B, kSortThreads, 0, st>>>(a));
+    YB_LAUNCH("graph_sort_kernel", st, graph_sort_kernel<<<dim3(B, 2), kSortThreads, 0, st>>>(a));
+    const dim3 ggrid((a.tcap + kGatherThreads / 32 - 1) / (kGatherThreads / 32), B);
+    YB_LAUNCH("graph_gather_kernel", st, graph_gather_kernel<<<ggrid, kGatherThreads, 0, st>>>(a));
     const int ctas = sm_count() * 4;
     YB_LAUNCH("graph_edge_kernel", st, graph_edge_kernel<<<ctas, kEdgeThreads, 0, st>>>(a));
     const size_t dyn = (size_t)((cap + 31) / 32) * 4 * 4;
@@ -507,6 +549,21 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     if (dyn > 40 * 1024)
         YB_CUDA(cudaFuncSetAttribute(graph_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     YB_LAUNCH("graph_resolve_kernel", st, graph_resolve_kernel<<<B, kResolveThreads, dyn, st>>>(a));
+    return 0;
+}
+
+int graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned long long* evals, unsigned long long* edges,
+                cudaStream_t st) {
+    GLayout L = graph_layout(B, cap);
+    YB_CHECK_ARG(ws && ws_bytes >= L.total, "nms_graph_stats: not a graph workspace");
+    std::vector<GImg> h((size_t)B);
+    YB_CUDA(cudaMemcpyAsync(h.data(), reinterpret_cast<const char*>(ws) + L.info, (size_t)B * sizeof(GImg),
+                            cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    unsigned long long ev = 0, ed = 0;
+    for (auto& g : h) { ev += g.n_evals; ed += g.n_edges; }
+    if (evals) *evals = ev;
+    if (edges) *edges = ed;
     return 0;
 }
 

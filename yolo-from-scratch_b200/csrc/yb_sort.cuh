@@ -23,6 +23,20 @@ __device__ __forceinline__ u32 desc_key(float s) {
     return ~asc;
 }
 
+// Lanes of the warp holding the same 8-bit digit (valid lanes only).  Eight ballots instead of
+// match.any: MATCH issues at roughly one warp instruction per ~40 cycles per SM on sm_100 (the
+// round-1 profile of the sort kernel showed it bounding both phases), VOTE at the normal rate.
+__device__ __forceinline__ unsigned digit_peers(u32 d, bool valid) {
+    unsigned m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool p = (d >> bit) & 1u;
+        const unsigned v = __ballot_sync(0xffffffffu, p);
+        m &= p ? v : ~v;
+    }
+    return m;
+}
+
 // One pass on the 8-bit digit at `shift`.  Returns false (and writes nothing) when every key has
 // the same digit — the caller then keeps using the input buffers.
 __device__ inline bool radix_pass(const u32* __restrict__ kin, const u32* __restrict__ vin,
@@ -46,8 +60,8 @@ __device__ inline bool radix_pass(const u32* __restrict__ kin, const u32* __rest
 #pragma unroll
         for (int u = 0; u < kSortPrefetch; ++u) {
             const bool valid = (i0 + 32 * u + lane) < end;
-            const u32 d = valid ? ((key[u] >> shift) & 255u) : 0x1000u;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const u32 d = (key[u] >> shift) & 255u;
+            const unsigned peers = digit_peers(d, valid);
             if (valid && lane == (__ffs(peers) - 1)) h[d] += __popc(peers);
             __syncwarp();
         }
@@ -91,16 +105,18 @@ __device__ inline bool radix_pass(const u32* __restrict__ kin, const u32* __rest
 #pragma unroll
         for (int u = 0; u < kSortPrefetch; ++u) {
             const bool valid = (i0 + 32 * u + lane) < end;
-            const u32 d = valid ? ((key[u] >> shift) & 255u) : 0x1000u;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const u32 d = (key[u] >> shift) & 255u;
+            const unsigned peers = digit_peers(d, valid);
             const int rank = __popc(peers & ((1u << lane) - 1u));
+            u32 base = 0;
             if (valid) {
-                const u32 dst = h[d] + tot[d] + rank;
+                base = h[d];
+                const u32 dst = base + tot[d] + rank;
                 kout[dst] = key[u];
                 vout[dst] = val[u];
             }
             __syncwarp();
-            if (valid && lane == (__ffs(peers) - 1)) h[d] += __popc(peers);
+            if (valid && lane == (__ffs(peers) - 1)) h[d] = base + __popc(peers);
             __syncwarp();
         }
     }

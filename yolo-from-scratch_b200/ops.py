@@ -440,7 +440,7 @@ GRAPH_EDGES_PER_BOX = 16  # edge-list capacity of the default workspace (dense r
 
 
 def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel=TRICK_MAX_NUMEL_CUDA,
-                       algo=NMS_GRAPH):
+                       algo=NMS_GRAPH, return_workspace=False):
     """NMS for B images at once.  boxes (B,cap,4), scores (B,cap), classes (B,cap) int64 or None,
     counts (B,) int32 or None.  Returns (keep (B,cap) int64, n_keep (B,) int32) on the GPU, nothing
     synchronised.  With the default sparse-graph algorithm an image whose suppression graph does
@@ -459,7 +459,23 @@ def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_
     _lib.check(L.yb_batched_nms(boxes.data_ptr(), scores.data_ptr(), _ptr(classes), _ptr(counts), B, cap,
                                 float(iou_threshold), int(trick_max_numel), int(algo), keep.data_ptr(),
                                 n_keep.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "yb_batched_nms")
+    if return_workspace:
+        return keep, n_keep, ws
     return keep, n_keep
+
+
+def nms_graph_stats(det):
+    """(8-pair evaluations, edges) of the graph NMS behind a `detect_batch` result, summed over the
+    batch; None for the bitmask algorithm.  Synchronises.  For bench.py / tests."""
+    ws = det.get("nms_ws")
+    if ws is None or det.get("algo", NMS_GRAPH) != NMS_GRAPH:
+        return None
+    B, cap = det["boxes"].shape[0], det["boxes"].shape[1]
+    ev, ed = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    with torch.cuda.device(ws.device):
+        _lib.check(_lib.lib().yb_nms_graph_stats(ws.data_ptr(), ws.numel(), B, cap, ctypes.byref(ev), ctypes.byref(ed),
+                                                 _stream()), "yb_nms_graph_stats")
+    return int(ev.value), int(ed.value)
 
 
 def nms_retry_overflow(boxes, scores, classes, counts, iou_threshold, trick_max_numel, keep, n_keep):
@@ -525,9 +541,10 @@ def detect_batch(predictions, anchors_list, img_size, num_classes=1, conf_thresh
     boxes, scores, classes, counts = filter_candidates(predictions, anchors_list, img_size, num_classes,
                                                        conf_threshold, letterbox)
     with torch.cuda.device(boxes.device):
-        keep, n_keep = batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel, algo)
+        keep, n_keep, ws = batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel, algo,
+                                              return_workspace=True)
     return {"boxes": boxes, "scores": scores, "classes": classes, "counts": counts, "keep": keep, "n_keep": n_keep,
-            "iou_threshold": float(iou_threshold), "trick_max_numel": int(trick_max_numel)}
+            "iou_threshold": float(iou_threshold), "trick_max_numel": int(trick_max_numel), "algo": algo, "nms_ws": ws}
 
 
 def pack_detections(det):
