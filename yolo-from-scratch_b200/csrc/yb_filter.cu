@@ -4,32 +4,40 @@
 //
 // Bound: HBM.  Algorithmic bytes: rows*min(row_bytes,32) for the objectness column,
 // plus M*row_bytes for the rows that pass and 28*M for the candidate list.
-// Two launches:
-//   filter_count_kernel  one objectness test per row, per-tile pass counts
+// A tile is 128 consecutive rows of one scale of one image; a CTA owns a GROUP of G consecutive
+// tiles (G = 1 for 85-float rows, 8 for 6-float rows: ~24-44 KB of head data per CTA), so that
+// every thread has G independent loads in flight.  Two launches:
+//   filter_count_kernel  objectness test, pass count per tile
 //   filter_emit_kernel   per-image exclusive prefix over the tile counts (order preserving),
 //                        in-tile ballot scan, and for the passing rows decode + class max +
-//                        box build.  Dense tiles are staged in shared memory with coalesced
-//                        128-bit loads (row stride 5+nc words; conflict-free when odd).
+//                        box build.  Dense groups are staged in shared memory by ONE bulk-async
+//                        copy (cp.async.bulk, mbarrier completion): the rows of a group are
+//                        contiguous in the head tensor, so the whole group is a single 1-D TMA
+//                        transfer and several CTAs per SM keep >100 KB in flight.  Rows are
+//                        then read at stride 5+nc words (odd for nc=80: conflict-free).
 #include "yb_common.cuh"
 
 namespace yb {
 
-constexpr int kFTile = 128;  // rows per tile == threads per CTA
+constexpr int kFTile = 128;    // rows per tile == threads per CTA
+constexpr int kFMaxGroup = 8;  // tiles per CTA, at most
 
 struct FilterScale {
     const float* pred;
     const float* anchors;
-    uint32_t rows;        // rows per image at this scale = H*W*A
-    uint32_t tile_begin;  // first tile (within an image) of this scale
+    uint32_t rows;         // rows per image at this scale = H*W*A
+    uint32_t tile_begin;   // first tile (within an image) of this scale
+    uint32_t group_begin;  // first group (within an image) of this scale
     float inv_w, inv_h;
     FastDiv d_A, d_W;
 };
 
 struct FilterArgs {
-    int S, A, nc, cap;
-    uint32_t row, tiles_per_img;
+    int S, A, nc, cap, G;
+    uint32_t row, tiles_per_img, groups_per_img;
     float img, inv_img, conf;
     int stage_ok;              // shared-memory staging available for this row length
+    uint32_t sobj_offset;      // float offset of the sigmoid(obj) scratch in dynamic shared memory
     const float* letterbox;    // (B,3) scale, pad_top, pad_left or null
     FilterScale sc[YB_MAX_SCALES];
     int* tile_counts;          // (B, tiles_per_img)
@@ -39,134 +47,225 @@ struct FilterArgs {
     int* counts;
 };
 
-__device__ __forceinline__ int tile_scale(const FilterArgs& a, uint32_t tile) {
+__device__ __forceinline__ int group_scale(const FilterArgs& a, uint32_t group) {
     int s = 0;
 #pragma unroll
     for (int k = 1; k < YB_MAX_SCALES; ++k)
-        if (k < a.S && tile >= a.sc[k].tile_begin) s = k;
+        if (k < a.S && group >= a.sc[k].group_begin) s = k;
     return s;
 }
 
 __global__ void __launch_bounds__(kFTile) filter_count_kernel(const FilterArgs a) {
-    const uint32_t tile = blockIdx.x, b = blockIdx.y;
-    const FilterScale& L = a.sc[tile_scale(a, tile)];
-    const uint32_t r = (tile - L.tile_begin) * kFTile + threadIdx.x;
-    bool pass = false;
-    if (r < L.rows) {
-        const float x = __ldg(L.pred + ((size_t)b * L.rows + r) * a.row + 4);
-        pass = sigmoidf_ref(x) > a.conf;  // :1157,:1166-1167 objectness only
+    const uint32_t group = blockIdx.x, b = blockIdx.y;
+    const FilterScale& L = a.sc[group_scale(a, group)];
+    const uint32_t tile0 = (group - L.group_begin) * a.G;        // tile within the scale
+    const uint32_t ntiles = (L.rows + kFTile - 1) / kFTile;
+    const float* col = L.pred + (size_t)b * L.rows * a.row + 4;  // objectness column
+    float x[kFMaxGroup];
+#pragma unroll
+    for (int k = 0; k < kFMaxGroup; ++k) {
+        const uint32_t r = (tile0 + k) * kFTile + threadIdx.x;
+        x[k] = (k < a.G && r < L.rows) ? __ldg(col + (size_t)r * a.row) : -INFINITY;
     }
-    const int n = __syncthreads_count(pass);
-    if (threadIdx.x == 0) a.tile_counts[b * a.tiles_per_img + tile] = n;
+#pragma unroll
+    for (int k = 0; k < kFMaxGroup; ++k) {
+        if (k >= a.G || tile0 + k >= ntiles) break;  // uniform
+        const bool pass = sigmoidf_ref(x[k]) > a.conf;  // :1157,:1166-1167 objectness only
+        const int n = __syncthreads_count(pass);
+        if (threadIdx.x == 0) a.tile_counts[b * a.tiles_per_img + L.tile_begin + tile0 + k] = n;
+    }
 }
 
 // first index of the maximum of sigmoid(x[0..nc)) — torch.max(dim=1) semantics (:1189).
-// sigmoid is monotone, so the maximum is sigmoid(max logit); an earlier, smaller logit can
-// only tie after fp32 rounding if it lies within 1.0 of min(max logit, 14).
+// sigmoid is monotone, so the maximum is sigmoid(max logit) and its index is the first maximal
+// logit, unless an EARLIER, smaller logit v rounds to the same fp32 probability.  Since
+// d/dx ln sigmoid(x) = sigmoid(-x) >= sigmoid(-m) on (-inf, m], two logits whose probabilities
+// agree to within k fp32 ulps satisfy m - v <= k * 2^-23 * (1 + e^m); the evaluation error of
+// 1/(1+expf(-x)) is below 4 ulp, so k = 16 is safe and only logits above
+// lo = m - 2e-6*(1+e^m) are re-evaluated (m <= 14; above that sigmoid saturates and every logit
+// above 13 is re-evaluated).  On random heads the re-evaluation practically never runs, which keeps
+// the warp converged (the round-1 kernel used a window of 1.0 and spent ~80% of its instructions in
+// divergent sigmoid re-evaluations).
 template <typename Load>
 __device__ __forceinline__ void class_max(int nc, Load ld, float& prob, int& id) {
     float m = ld(0);
-    int mi = 0;
-    for (int c = 1; c < nc; ++c) {
+    int mi = 0, c = 1;
+    for (; c + 4 <= nc; c += 4) {  // 4 independent loads per step
+        const float v0 = ld(c), v1 = ld(c + 1), v2 = ld(c + 2), v3 = ld(c + 3);
+        if (v0 > m) { m = v0; mi = c; }
+        if (v1 > m) { m = v1; mi = c + 1; }
+        if (v2 > m) { m = v2; mi = c + 2; }
+        if (v3 > m) { m = v3; mi = c + 3; }
+    }
+    for (; c < nc; ++c) {
         const float v = ld(c);
         if (v > m) { m = v; mi = c; }
     }
     prob = sigmoidf_ref(m);
     id = mi;
-    const float lo = fminf(m, 14.0f) - 1.0f;
-    for (int c = 0; c < mi; ++c) {
+    const float lo = (m <= 14.0f) ? m - 2e-6f * (1.0f + expf(m)) : 13.0f;
+    for (c = 0; c < nc; ++c) {  // near-ties on either side of mi (expf need not be monotone to the last ulp)
         const float v = ld(c);
-        if (v > lo && sigmoidf_ref(v) == prob) { id = c; break; }
+        if (v > lo && c != mi) {
+            const float p = sigmoidf_ref(v);
+            if (p > prob || (p == prob && c < id)) { prob = p; id = c; }
+        }
     }
 }
 
+// ---- bulk-async (TMA 1-D) staging ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
 __global__ void __launch_bounds__(kFTile) filter_emit_kernel(const FilterArgs a) {
-    extern __shared__ float s_tile[];
+    extern __shared__ __align__(128) float s_tile[];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_red[kFTile / 32];
-    __shared__ int s_wbase[kFTile / 32];
-    const uint32_t tile = blockIdx.x, b = blockIdx.y;
+    __shared__ int s_wcnt[kFMaxGroup][kFTile / 32];
+    __shared__ unsigned s_bal[kFMaxGroup][kFTile / 32];
+    __shared__ int s_cnt[kFMaxGroup];
+    // sigmoid(obj) of this thread's row in every tile of the group lives behind the staged rows
+    float(*s_sobj)[kFTile] = reinterpret_cast<float(*)[kFTile]>(s_tile + a.sobj_offset);
+    const uint32_t group = blockIdx.x, b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = group_scale(a, group);
+    const FilterScale& L = a.sc[s];
+    const uint32_t tile0 = (group - L.group_begin) * a.G;  // within the scale
+    const uint32_t ntiles = (L.rows + kFTile - 1) / kFTile;
+    const int G = (int)min((uint32_t)a.G, ntiles - tile0);  // tiles of this group
+    const uint32_t first_tile = L.tile_begin + tile0;       // within the image
     const int* tc = a.tile_counts + b * a.tiles_per_img;
 
-    // exclusive prefix of this tile within its image
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+
+    // exclusive prefix of this group within its image, and the group's own counts
     int part = 0;
-    for (uint32_t t = threadIdx.x; t < tile; t += kFTile) part += tc[t];
+    for (uint32_t t = threadIdx.x; t < first_tile; t += kFTile) part += tc[t];
     part = __reduce_add_sync(0xffffffffu, part);
     if (lane == 0) s_red[warp] = part;
     __syncthreads();
     int prefix = 0;
 #pragma unroll
     for (int k = 0; k < kFTile / 32; ++k) prefix += s_red[k];
-    const int count = tc[tile];
-    if (tile == a.tiles_per_img - 1 && threadIdx.x == 0) {
-        const int tot = prefix + count;
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < kFMaxGroup; ++k) {
+        const int c = k < G ? tc[first_tile + k] : 0;
+        if (threadIdx.x == 0) s_cnt[k] = c;
+        total += c;
+    }
+    if (first_tile + G == a.tiles_per_img && threadIdx.x == 0) {
+        const int tot = prefix + total;
         a.counts[b] = tot < a.cap ? tot : a.cap;
     }
-    if (count == 0) return;
+    if (total == 0) return;
 
-    const int s = tile_scale(a, tile);
-    const FilterScale& L = a.sc[s];
-    const uint32_t row0 = (tile - L.tile_begin) * kFTile;
-    const uint32_t nrows = min((uint32_t)kFTile, L.rows - row0);
-    const size_t base = ((size_t)b * L.rows + row0) * a.row;  // float offset of the tile
+    const uint32_t row0 = tile0 * kFTile;
+    const uint32_t nrows = min((uint32_t)(G * kFTile), L.rows - row0);
+    const size_t base = ((size_t)b * L.rows + row0) * a.row;  // float offset of the group
     const float* g = L.pred + base;
 
-    // dense tiles of long rows: stage through shared memory with coalesced loads
-    const bool staged = a.stage_ok && a.row > 8 && count * 4 >= (int)nrows;
+    // dense groups: stage through shared memory
+    const bool staged = a.stage_ok && total * 4 >= (int)nrows;
     if (staged) {
         const uint32_t nfl = nrows * a.row;
-        if ((base & 3) == 0) {
-            const float4* g4 = reinterpret_cast<const float4*>(g);
-            float4* s4 = reinterpret_cast<float4*>(s_tile);
-            for (uint32_t v = threadIdx.x; v < (nfl >> 2); v += kFTile) s4[v] = __ldcs(g4 + v);
-            for (uint32_t e = (nfl & ~3u) + threadIdx.x; e < nfl; e += kFTile) s_tile[e] = g[e];
+        if ((base & 3) == 0 && (nfl & 3) == 0) {
+            if (threadIdx.x == 0) bulk_load(s_tile, g, nfl * 4u, &s_bar);
+            mbar_wait(&s_bar, 0);
         } else {
             for (uint32_t e = threadIdx.x; e < nfl; e += kFTile) s_tile[e] = g[e];
+            __syncthreads();
         }
-        __syncthreads();
     }
-    const float* x = staged ? (s_tile + threadIdx.x * a.row) : (g + (size_t)threadIdx.x * a.row);
 
-    bool pass = false;
-    float sobj = 0.0f;
-    if (threadIdx.x < nrows) {
-        sobj = sigmoidf_ref(x[4]);
-        pass = sobj > a.conf;
+    // phase A: objectness test of this thread's row in every tile of the group
+#pragma unroll 2
+    for (int k = 0; k < G; ++k) {
+        const uint32_t rl = k * kFTile + threadIdx.x;
+        bool pass = false;
+        float so = 0.0f;
+        if (rl < nrows) {
+            const float xo = staged ? s_tile[rl * a.row + 4] : __ldg(g + (size_t)rl * a.row + 4);
+            so = sigmoidf_ref(xo);
+            pass = so > a.conf;
+        }
+        s_sobj[k][threadIdx.x] = so;
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0) { s_wcnt[k][warp] = __popc(bal); s_bal[k][warp] = bal; }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) s_wbase[warp] = __popc(bal);
     __syncthreads();
-    int pos = prefix + __popc(bal & ((1u << lane) - 1));
-    for (int k = 0; k < warp; ++k) pos += s_wbase[k];
-    if (!pass || pos >= a.cap) return;
 
-    // decode (:1154) with the model's img_size
-    const uint32_t r = row0 + threadIdx.x;
-    uint32_t cell, an, gy, gx;
-    L.d_A.divmod(r, cell, an);
-    L.d_W.divmod(cell, gy, gx);
-    const float aw = __ldg(L.anchors + an * 2), ah = __ldg(L.anchors + an * 2 + 1);
-    const float bx = decode_xy(x[0], (float)gx, L.inv_w);
-    const float by = decode_xy(x[1], (float)gy, L.inv_h);
-    const float bw = decode_wh(x[2], aw, a.inv_img);
-    const float bh = decode_wh(x[3], ah, a.inv_img);
-    // class probability and id (:1184-1189)
-    float cprob;
-    int cid;
-    class_max(a.nc, [&](int c) { return x[5 + c]; }, cprob, cid);
-    // pixels, corners, letterbox reverse (:1192-1213)
-    const float xc = bx * a.img, yc = by * a.img, wp = bw * a.img, hp = bh * a.img;
-    float x1 = xc - wp * 0.5f, y1 = yc - hp * 0.5f, x2 = xc + wp * 0.5f, y2 = yc + hp * 0.5f;
+    // phase B: emit
+    float inv_s = 1.0f, pt = 0.0f, pl = 0.0f;
     if (a.letterbox) {
-        const float inv_s = 1.0f / a.letterbox[b * 3 + 0];
-        const float pt = a.letterbox[b * 3 + 1], pl = a.letterbox[b * 3 + 2];
-        x1 = (x1 - pl) * inv_s; y1 = (y1 - pt) * inv_s;
-        x2 = (x2 - pl) * inv_s; y2 = (y2 - pt) * inv_s;
+        inv_s = 1.0f / a.letterbox[b * 3 + 0];
+        pt = a.letterbox[b * 3 + 1];
+        pl = a.letterbox[b * 3 + 2];
     }
-    const size_t o = (size_t)b * a.cap + pos;
-    a.boxes[o] = make_float4(x1, y1, x2, y2);
-    a.scores[o] = sobj * cprob;  // :1216
-    a.classes[o] = (int64_t)cid;
+#pragma unroll 1
+    for (int k = 0; k < G; ++k) {
+        const unsigned bal = s_bal[k][warp];
+        const bool pass = (bal >> lane) & 1u;
+        int pos = prefix + __popc(bal & ((1u << lane) - 1));
+        for (int w = 0; w < warp; ++w) pos += s_wcnt[k][w];
+        prefix += s_cnt[k];
+        if (!pass || pos >= a.cap) continue;
+        const uint32_t rl = k * kFTile + threadIdx.x;
+        const uint32_t r = row0 + rl;
+        uint32_t cell, an, gy, gx;
+        L.d_A.divmod(r, cell, an);
+        L.d_W.divmod(cell, gy, gx);
+        const float aw = __ldg(L.anchors + an * 2), ah = __ldg(L.anchors + an * 2 + 1);
+        float x0, x1r, x2r, x3r, cprob;
+        int cid;
+        if (staged) {
+            const float* x = s_tile + rl * a.row;
+            x0 = x[0]; x1r = x[1]; x2r = x[2]; x3r = x[3];
+            class_max(a.nc, [&](int c) { return x[5 + c]; }, cprob, cid);
+        } else {
+            const float* x = g + (size_t)rl * a.row;
+            x0 = __ldg(x); x1r = __ldg(x + 1); x2r = __ldg(x + 2); x3r = __ldg(x + 3);
+            class_max(a.nc, [&](int c) { return __ldg(x + 5 + c); }, cprob, cid);
+        }
+        // decode (:1154) with the model's img_size
+        const float bx = decode_xy(x0, (float)gx, L.inv_w);
+        const float by = decode_xy(x1r, (float)gy, L.inv_h);
+        const float bw = decode_wh(x2r, aw, a.inv_img);
+        const float bh = decode_wh(x3r, ah, a.inv_img);
+        // pixels, corners, letterbox reverse (:1192-1213)
+        const float xc = bx * a.img, yc = by * a.img, wp = bw * a.img, hp = bh * a.img;
+        float x1 = xc - wp * 0.5f, y1 = yc - hp * 0.5f, x2 = xc + wp * 0.5f, y2 = yc + hp * 0.5f;
+        if (a.letterbox) {
+            x1 = (x1 - pl) * inv_s; y1 = (y1 - pt) * inv_s;
+            x2 = (x2 - pl) * inv_s; y2 = (y2 - pt) * inv_s;
+        }
+        const size_t o = (size_t)b * a.cap + pos;
+        a.boxes[o] = make_float4(x1, y1, x2, y2);
+        a.scores[o] = s_sobj[k][threadIdx.x] * cprob;  // :1216
+        a.classes[o] = (int64_t)cid;
+    }
 }
 
 static int filter_fill(const yb_heads_desc* d, FilterArgs& a) {
@@ -175,7 +274,13 @@ static int filter_fill(const yb_heads_desc* d, FilterArgs& a) {
                  "filter: bad S/B/A/nc (nc must be >= 1, train.py:1184-1189)");
     a.S = d->S; a.A = d->A; a.nc = d->nc; a.row = 5 + d->nc;
     a.img = d->img_size; a.inv_img = 1.0f / d->img_size;
-    uint32_t tile = 0;
+    // tiles per CTA: about 44 KB of head rows, at most kFMaxGroup
+    {
+        const size_t tile_bytes = (size_t)kFTile * a.row * sizeof(float);
+        size_t G = (44 * 1024) / tile_bytes;
+        a.G = (int)(G < 1 ? 1 : (G > (size_t)kFMaxGroup ? (size_t)kFMaxGroup : G));
+    }
+    uint32_t tile = 0, group = 0;
     for (int s = 0; s < d->S; ++s) {
         YB_CHECK_ARG(d->H[s] > 0 && d->W[s] > 0, "filter: bad grid at scale %d", s);
         unsigned long long n = (unsigned long long)d->B * d->H[s] * d->W[s] * d->A * (5 + d->nc);
@@ -184,11 +289,15 @@ static int filter_fill(const yb_heads_desc* d, FilterArgs& a) {
         L.pred = d->pred[s]; L.anchors = d->anchors[s];
         L.rows = (uint32_t)d->H[s] * d->W[s] * d->A;
         L.tile_begin = tile;
-        tile += (L.rows + kFTile - 1) / kFTile;
+        L.group_begin = group;
+        const uint32_t nt = (L.rows + kFTile - 1) / kFTile;
+        tile += nt;
+        group += (nt + a.G - 1) / a.G;
         L.inv_w = 1.0f / (float)d->W[s]; L.inv_h = 1.0f / (float)d->H[s];
         L.d_A = FastDiv(d->A); L.d_W = FastDiv(d->W[s]);
     }
     a.tiles_per_img = tile;
+    a.groups_per_img = group;
     return 0;
 }
 
@@ -220,12 +329,16 @@ extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const
     a.cap = cap; a.conf = conf_thres; a.letterbox = letterbox;
     a.tile_counts = reinterpret_cast<int*>(ws);
     a.boxes = reinterpret_cast<float4*>(boxes); a.scores = scores; a.classes = classes; a.counts = counts;
-    const size_t smem = (size_t)kFTile * a.row * sizeof(float);
+    size_t smem = (size_t)a.G * kFTile * a.row * sizeof(float);
     a.stage_ok = smem <= 200 * 1024;
+    if (!a.stage_ok) smem = 0;
+    smem = (smem + 15) / 16 * 16;
+    a.sobj_offset = (uint32_t)(smem / sizeof(float));
+    smem += (size_t)a.G * kFTile * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(a.tiles_per_img, d->B);
+    dim3 grid(a.groups_per_img, d->B);
     YB_LAUNCH("filter_count_kernel", st, filter_count_kernel<<<grid, kFTile, 0, st>>>(a));
-    const size_t dyn = (a.stage_ok && a.row > 8) ? smem : 0;
+    const size_t dyn = smem;
     if (dyn > 48 * 1024)
         YB_CUDA(cudaFuncSetAttribute(filter_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     YB_LAUNCH("filter_emit_kernel", st, filter_emit_kernel<<<grid, kFTile, dyn, st>>>(a));

@@ -31,6 +31,7 @@ namespace yb {
 constexpr int kTile = 32;
 constexpr int kSub = 8;             // columns per sub-tile (row culling granularity)
 constexpr int kSubs = kTile / kSub;
+constexpr uint32_t kNoSub = 0xffffffffu;
 constexpr int kGatherThreads = 256;
 constexpr int kEdgeThreads = 256;
 constexpr int kResolveThreads = 1024;
@@ -257,16 +258,133 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
 // ------------------------------------------------------------------------------------------------
 struct RowAux { u32 rank; u32 cls; };
 
-__global__ void __launch_bounds__(kEdgeThreads) graph_edge_kernel(const GArgs a) {
-    __shared__ float4 s_row[kEdgeThreads / 32][kTile];
-    __shared__ float s_area[kEdgeThreads / 32][kTile];
-    __shared__ RowAux s_aux[kEdgeThreads / 32][kTile];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int grp = lane / kSub;  // this lane's column sub-tile
+// Per-warp shared memory of the edge kernel.
+struct EdgeWarp {
+    float4 row[kTile];      // rows of tile I
+    float4 col[kTile];      // columns of the current chunk: 4 surviving sub-tiles x 8 boxes
+    float rarea[kTile];
+    float carea[kTile];
+    RowAux raux[kTile];
+    u32 tl[kTile];          // compaction scratch: surviving tiles of the current step
+    u32 sub[kTile * kSubs + 8];  // queue of surviving sub-tile ids (J*kSubs+s); < 4 left over between steps
+    unsigned char item[kTile * kSubs];  // (sub-tile slot << 5) | row, packed work list of a chunk
+};
+
+// One chunk = up to 4 sub-tiles (8 columns each) that survived the tile-level tests against row
+// tile I.  Lane l holds column (l&7) of slot (l>>3).  Rows are culled against each slot's
+// statistics, the surviving (row, slot) items are packed, and every iteration of the pair loop
+// evaluates 4 items x 8 columns: all 32 lanes busy whatever the culling pattern.
+__device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I, int head,
+                                           const float4* __restrict__ sb, const u32* __restrict__ srank,
+                                           const u32* __restrict__ scls, const float4* __restrict__ ss,
+                                           uint2* __restrict__ edges, const float4 rq, const bool rvalid,
+                                           const float rw_t, const float rh_t, const float rS, const float rS_t,
+                                           u32& n_evals) {
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / kSub;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const u32 total = (u32)a.tcap * (u32)a.B;
     const float kEps = 9.5367431640625e-07f;     // 2^-20
     const float kTiny = 7.888609052210118e-31f;  // 2^-100
+    const float far = 3.0e38f;
+    const int M = info.M;
+    const bool prune = info.t2 >= 0.0f;
+    const float t2 = info.t2;
+    const bool class_mode = info.mode == G_CLASS;
+    const bool all_exact = info.exact != 0;
+
+    // this lane's column
+    const u32* sub = w.sub + head;  // the chunk's four sub-tile ids (kNoSub = empty slot)
+    const u32 my_sub = sub[grp];
+    const bool slot_ok = my_sub != kNoSub;
+    const int cp = slot_ok ? (int)(my_sub * kSub) + (lane & (kSub - 1)) : 0;
+    const bool cvalid = slot_ok && cp < M;
+    float4 cq = make_float4(far, far, far, far);
+    if (cvalid) cq = sb[cp];
+    const float cw = cq.z - cq.x, ch = cq.w - cq.y;
+    w.col[lane] = cq;
+    w.carea[lane] = cw * ch;
+
+    // row culling against the statistics of each slot; pack the surviving (row, slot) items
+    int n_items = 0;
+#pragma unroll
+    for (int s = 0; s < kSubs; ++s) {
+        const u32 e = sub[s];
+        bool rok = rvalid && e != kNoSub;
+        if (rok) {
+            if (prune) {
+                const float4 sbx = ss[e * 2], sar = ss[e * 2 + 1];
+                const float ox = fminf(rq.z, sbx.z) - fmaxf(rq.x, sbx.x);
+                const float oy = fminf(rq.w, sbx.w) - fmaxf(rq.y, sbx.y);
+                rok = ox > 0.0f && oy > 0.0f && ox >= rw_t && oy >= rh_t && sar.y >= rS_t && rS >= t2 * sar.x;
+            } else {
+                rok = (int)(e * kSub) < M;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, rok);
+        if (rok) w.item[n_items + __popc(m & lt_mask)] = (unsigned char)((s << 5) | lane);
+        n_items += __popc(m);
+    }
+    n_evals += (u32)n_items;
+    __syncwarp();
+
+    for (int it = 0; it < n_items; it += kSubs) {
+        const int idx = it + grp;
+        const bool act = idx < n_items;
+        const u32 item = w.item[act ? idx : it];
+        const int i = item & 31u, slot = item >> 5;
+        const int c = slot * kSub + (lane & (kSub - 1));
+        const float4 r = w.row[i];
+        const float rarea = w.rarea[i];
+        const float4 q = w.col[c];
+        const float qarea = w.carea[c];
+        const float left = fmaxf(r.x, q.x), right = fminf(r.z, q.z);
+        const float top = fmaxf(r.y, q.y), bottom = fminf(r.w, q.w);
+        const float iw = fmaxf(right - left, 0.0f), ih = fmaxf(bottom - top, 0.0f);
+        const float inter = iw * ih;
+        // den within a few ulp of torchvision's fma form whichever box plays `a`: inside the margin
+        const float den0 = (qarea + rarea) - inter;
+        const float tt = a.thr * den0;
+        const float d = inter - tt;
+        bool pr = act && d > 0.0f;
+        const bool amb = act && (all_exact || !(fabsf(d) > __fmaf_rn(tt, kEps, kTiny)));
+        if (!__any_sync(0xffffffffu, pr || amb)) continue;
+        // rare: a candidate edge.  Exact arithmetic where needed, validity, same class, each pair once.
+        const RowAux ra = w.raux[i];
+        const int qp = (int)(sub[slot] * kSub) + (lane & (kSub - 1));
+        const bool qvalid = act && qp < M;
+        u32 crank = 0xffffffffu, ccls = 0u;
+        if (qvalid) { crank = srank[qp]; ccls = scls[qp]; }
+        if (amb) {
+            // torchvision devIoU with a = the higher-scored box
+            const bool row_a = ra.rank < crank;
+            const float qw = q.z - q.x, qh = q.w - q.y;
+            const float sa = row_a ? rarea : qarea;
+            const float bw = row_a ? qw : (r.z - r.x), bh = row_a ? qh : (r.w - r.y);
+            const float den = __fmaf_rn(bw, bh, sa) - inter;
+            pr = (inter / den) > a.thr;
+        }
+        const bool fin = pr && qvalid && (!class_mode || ccls == ra.cls) && qp > I * kTile + i;
+        const unsigned em = __ballot_sync(0xffffffffu, fin);
+        if (em) {
+            const int leader = __ffs(em) - 1;
+            u32 base = 0;
+            if (lane == leader) base = atomicAdd(&a.info[b].n_edges, (u32)__popc(em));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (fin) {
+                const u64 k = (u64)base + __popc(em & lt_mask);
+                if (k < a.edges_per_img) edges[k] = make_uint2(min(ra.rank, crank), max(ra.rank, crank));
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kEdgeThreads, 3) graph_edge_kernel(const GArgs a) {
+    __shared__ EdgeWarp s_w[kEdgeThreads / 32];
+    const int lane = threadIdx.x & 31;
+    EdgeWarp& w = s_w[threadIdx.x >> 5];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const u32 total = (u32)a.tcap * (u32)a.B;
     const float far = 3.0e38f;
 
     for (;;) {
@@ -288,7 +406,6 @@ __global__ void __launch_bounds__(kEdgeThreads) graph_edge_kernel(const GArgs a)
         const bool prune = info.t2 >= 0.0f;
         const float t2 = info.t2;
         const bool class_mode = info.mode == G_CLASS;
-        const bool all_exact = info.exact != 0;
 
         // this lane's row of tile I
         const int rp = I * kTile + lane;
@@ -300,101 +417,78 @@ __global__ void __launch_bounds__(kEdgeThreads) graph_edge_kernel(const GArgs a)
         const float rS = rw * rh;
         const float rw_t = t2 * rw, rh_t = t2 * rh, rS_t = t2 * rS;
         __syncwarp();
-        s_row[warp][lane] = rq;
-        s_area[warp][lane] = rS;
-        s_aux[warp][lane] = RowAux{rrank, rcls};
+        w.row[lane] = rq;
+        w.rarea[lane] = rS;
+        w.raux[lane] = RowAux{rrank, rcls};
         __syncwarp();
         const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
-        const u32 icmax = __float_as_uint(ia.w);
+        const u32 icmin = __float_as_uint(ia.z), icmax = __float_as_uint(ia.w);
         u32 n_evals = 0;
+        int n_q = 0;  // sub-tiles waiting in w.sub
 
-        for (int J0 = I; J0 < info.n_tiles; J0 += 32) {
-            const int Jl = J0 + lane;
-            bool ok = Jl < info.n_tiles;
-            float4 jb = make_float4(0.f, 0.f, 0.f, 0.f), ja = jb;
-            if (ok) { jb = ts[Jl * 2]; ja = ts[Jl * 2 + 1]; }
-            if (class_mode) {
-                // tiles are ordered by class: nothing beyond the last tile that can hold icmax
-                const bool beyond = ok && __float_as_uint(ja.z) > icmax;
-                ok = ok && !beyond && __float_as_uint(ja.w) >= __float_as_uint(ia.z);
-                if (__ballot_sync(0xffffffffu, beyond) == 0xffffffffu) break;
-            }
-            if (ok && prune) {
-                ok = fminf(ib.z, jb.z) > fmaxf(ib.x, jb.x) && fminf(ib.w, jb.w) > fmaxf(ib.y, jb.y) &&
-                     ia.y >= t2 * ja.x && ja.y >= t2 * ia.x;
-            }
-            unsigned cand = __ballot_sync(0xffffffffu, ok);
-            while (cand) {
-                const int jl = __ffs(cand) - 1;
-                cand &= cand - 1u;
-                const int J = J0 + jl;
-                // this lane's column of tile J
-                const int cp = J * kTile + lane;
-                const bool cvalid = cp < M;
-                float4 cq = make_float4(far, far, far, far);
-                if (cvalid) cq = sb[cp];
-                const float cw = cq.z - cq.x, ch = cq.w - cq.y;
-                // row culling: lane <-> row of tile I against the statistics of each 8-column sub-tile of J;
-                // this lane keeps the queue of rows that survive against ITS sub-tile
-                unsigned q = 0u;
-#pragma unroll
-                for (int s = 0; s < kSubs; ++s) {
-                    bool rok = rvalid;
-                    if (prune) {
-                        const float4 sbx = ss[(J * kSubs + s) * 2], sar = ss[(J * kSubs + s) * 2 + 1];
-                        const float ox = fminf(rq.z, sbx.z) - fmaxf(rq.x, sbx.x);
-                        const float oy = fminf(rq.w, sbx.w) - fmaxf(rq.y, sbx.y);
-                        rok = rok && ox > 0.0f && oy > 0.0f && ox >= rw_t && oy >= rh_t && sar.y >= rS_t &&
-                              rS >= t2 * sar.x;
-                    } else {
-                        rok = rok && (J * kTile + s * kSub) < M;
+        for (int J0 = I;; J0 += 32) {
+            const bool tail = J0 >= info.n_tiles;  // one extra round flushes the last partial chunk
+            if (tail) {
+                if (n_q == 0) break;
+                if (lane >= n_q && lane < kSubs) w.sub[lane] = kNoSub;
+                n_q = kSubs;
+                __syncwarp();
+            } else {
+                // level 1: lane <-> tile J
+                const int Jl = J0 + lane;
+                bool ok = Jl < info.n_tiles;
+                float4 jb = make_float4(0.f, 0.f, 0.f, 0.f), ja = jb;
+                if (ok) { jb = ts[Jl * 2]; ja = ts[Jl * 2 + 1]; }
+                if (class_mode) {
+                    // tiles are ordered by class: nothing beyond the last tile that can hold icmax
+                    const bool beyond = ok && __float_as_uint(ja.z) > icmax;
+                    ok = ok && !beyond && __float_as_uint(ja.w) >= icmin;
+                    if (__ballot_sync(0xffffffffu, beyond) == 0xffffffffu) {
+                        J0 = info.n_tiles - 32;  // next round is the tail
+                        continue;
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, rok);
-                    n_evals += __popc(m);
-                    if (s == grp) q = m;
                 }
-                while (__any_sync(0xffffffffu, q != 0u)) {
-                    const bool act = q != 0u;
-                    const int i = act ? (__ffs(q) - 1) : 0;
-                    q &= q - 1u;
-                    const float4 r = s_row[warp][i];
-                    const float rarea = s_area[warp][i];
-                    const float left = fmaxf(r.x, cq.x), right = fminf(r.z, cq.z);
-                    const float top = fmaxf(r.y, cq.y), bottom = fminf(r.w, cq.w);
-                    const float w = fmaxf(right - left, 0.0f), h = fmaxf(bottom - top, 0.0f);
-                    const float inter = w * h;
-                    // row taken as `a`; the true roles change den by <= 2 ulp, inside the margin
-                    const float den0 = __fmaf_rn(cw, ch, rarea) - inter;
-                    const float tt = a.thr * den0;
-                    const float d = inter - tt;
-                    bool pr = act && d > 0.0f;
-                    const bool amb = act && (all_exact || !(fabsf(d) > __fmaf_rn(tt, kEps, kTiny)));
-                    if (!__any_sync(0xffffffffu, pr || amb)) continue;
-                    // rare: a candidate edge.  Exact arithmetic where needed, validity, same class, dedup.
-                    const RowAux ra = s_aux[warp][i];
-                    u32 crank = 0xffffffffu, ccls = 0u;
-                    if (cvalid) { crank = srank[cp]; ccls = scls[cp]; }
-                    if (amb) {
-                        // torchvision devIoU with a = the higher-scored box
-                        const bool row_a = ra.rank < crank;
-                        const float sa = row_a ? rarea : cw * ch;
-                        const float bw = row_a ? cw : (r.z - r.x), bh = row_a ? ch : (r.w - r.y);
-                        const float den = __fmaf_rn(bw, bh, sa) - inter;
-                        pr = (inter / den) > a.thr;
-                    }
-                    const bool fin = pr && cvalid && (!class_mode || ccls == ra.cls) && (J != I || lane > i);
-                    const unsigned em = __ballot_sync(0xffffffffu, fin);
-                    if (em) {
-                        const int leader = __ffs(em) - 1;
-                        u32 base = 0;
-                        if (lane == leader) base = atomicAdd(&a.info[b].n_edges, (u32)__popc(em));
-                        base = __shfl_sync(0xffffffffu, base, leader);
-                        if (fin) {
-                            const u64 k = (u64)base + __popc(em & lt_mask);
-                            if (k < a.edges_per_img) edges[k] = make_uint2(min(ra.rank, crank), max(ra.rank, crank));
+                if (ok && prune) {
+                    ok = fminf(ib.z, jb.z) > fmaxf(ib.x, jb.x) && fminf(ib.w, jb.w) > fmaxf(ib.y, jb.y) &&
+                         ia.y >= t2 * ja.x && ja.y >= t2 * ia.x;
+                }
+                const unsigned cand = __ballot_sync(0xffffffffu, ok);
+                if (cand == 0u) continue;
+                if (ok) w.tl[__popc(cand & lt_mask)] = (u32)Jl;
+                __syncwarp();
+                const int n_t = __popc(cand);
+                // level 2: lane <-> (surviving tile, sub-tile), 8 tiles per step
+                for (int t0 = 0; t0 < n_t; t0 += 32 / kSubs) {
+                    const int k = t0 + lane / kSubs;
+                    bool sok = k < n_t;
+                    u32 e = 0u;
+                    if (sok) {
+                        e = w.tl[k] * kSubs + (u32)(lane & (kSubs - 1));
+                        sok = (int)(e * kSub) < M;
+                        if (sok && prune) {
+                            const float4 sbx = ss[e * 2], sar = ss[e * 2 + 1];
+                            sok = fminf(ib.z, sbx.z) > fmaxf(ib.x, sbx.x) && fminf(ib.w, sbx.w) > fmaxf(ib.y, sbx.y) &&
+                                  ia.y >= t2 * sar.x && sar.y >= t2 * ia.x;
                         }
                     }
+                    const unsigned sm = __ballot_sync(0xffffffffu, sok);
+                    if (sok) w.sub[n_q + __popc(sm & lt_mask)] = e;
+                    n_q += __popc(sm);
                 }
+                __syncwarp();
+            }
+            // level 3: chunks of 4 sub-tiles
+            int head = 0;
+            for (; n_q - head >= kSubs; head += kSubs)
+                edge_chunk(a, w, info, b, I, head, sb, srank, scls, ss, edges, rq, rvalid, rw_t, rh_t, rS, rS_t, n_evals);
+            if (head) {  // move the < 4 leftovers to the front
+                const int rem = n_q - head;
+                u32 v = 0u;
+                if (lane < rem) v = w.sub[head + lane];
+                __syncwarp();
+                if (lane < rem) w.sub[lane] = v;
+                __syncwarp();
+                n_q = rem;
             }
         }
         if (lane == 0 && n_evals) atomicAdd(&a.info[b].n_evals, (unsigned long long)n_evals);
