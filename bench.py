@@ -268,7 +268,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     weights = ops.MULTISCALE_OBJ_WEIGHTS
 
     # n_sets input sets per rank, on the device and (full run) mirrored in pinned host memory
-    dev_sets, host_sets = [], []
+    dev_sets, host_sets, label_sets = [], [], []
     for k in range(n_sets):
         seed = 1234 + 1000 * k + 100000 * rank
         heads = make_heads(B, img, nc, seed)
@@ -278,6 +278,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         dev_sets.append((d_heads, tg))
         if full:
             host_sets.append(([h.pin_memory() for h in heads], [t.cpu().pin_memory() for t in tg]))
+            label_sets.append(ops.pack_labels_host(labels, img, pin=True))
         del heads
     torch.cuda.synchronize()
     T_bytes = tensor_bytes(dev_sets[0][0])
@@ -370,10 +371,12 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         k["share"] = k["ms_per_step"] / ksum if ksum else 0.0
 
     # ---- e2e through the public API with host buffers ---------------------------------------------
-    e2e = None
+    e2e = e2e_labels = None
     if full:
         e2e = run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier,
                       max_over_ranks)
+        e2e_labels = run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier,
+                             max_over_ranks, label_sets=label_sets)
 
     # ---- variants: other confidence thresholds (device-resident, detect only) ---------------------
     variants = {}
@@ -483,7 +486,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         "config": workload_config(args, world, n_sets),
         "loss_fwd_bwd_ms": loss_ms, "decode_nms_ms": det_ms, "decode_nms_images_per_s": B * world / (det_ms * 1e-3),
         "candidates_per_image": float(np.mean(cand_counts)) / B, "kept_per_image": float(np.mean(keep_counts)) / B,
-        "e2e": e2e, "gpu_launches": int(launches), "kernels": kernels,
+        "e2e": e2e, "e2e_labels": e2e_labels, "gpu_launches": int(launches), "kernels": kernels,
         "roofline": roofline, "hbm_kernels": hbm_kernels, "roofline_nms": nms_roof, "cpu_baseline": cpu_baseline,
         "torch_gpu_baseline": torch_gpu, "clocks": clocks, "variants": variants,
     }
@@ -491,51 +494,111 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     return line
 
 
-def run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier, max_over_ranks):
-    """Same step through the public API with pinned HOST buffers: H2D of heads + dense targets, loss
-    fwd+bwd, detect, pack, D2H of the 4 losses and the detection rows — all inside the timed region."""
+def run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier, max_over_ranks,
+            label_sets=None):
+    """The same step through the public API with pinned HOST buffers.  Every step copies its inputs
+    host->device (heads + dense targets for the reference-signature call; heads + packed label lists
+    for the sparse-target call when `label_sets` is given), runs loss fwd+bwd, detect and pack, and
+    copies the 4 losses and the detection rows device->host — all inside the timed region.  Copies and
+    kernels are pipelined over two input slots (copy stream / compute stream / result stream): step
+    i+1's inputs travel while step i computes, as a training loop's prefetching loader does."""
     B, img, nc = args.batch, args.img, args.nc
-    loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
-    off_host = torch.empty(B + 1, dtype=torch.int32).pin_memory()
-    det_host = torch.empty(B * sum(G * G * 3 for G in grids), 6, dtype=torch.float32).pin_memory()
-    h2d = tensor_bytes(host_sets[0][0]) + tensor_bytes(host_sets[0][1])
+    comp = torch.cuda.current_stream()
+    h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    n_slots = 2
+    slots = []
+    for k in range(n_slots):
+        heads_d = [torch.empty_like(h, device=dev) for h in host_sets[0][0]]
+        if label_sets is None:
+            tg_d = [torch.empty_like(t, device=dev) for t in host_sets[0][1]]
+        else:
+            lab, n_gt, lb = label_sets[0]
+            tg_d = ops.PackedLabels(torch.empty_like(lab, device=dev), torch.empty_like(n_gt, device=dev),
+                                    torch.empty_like(lb, device=dev), img)
+        slots.append({"heads": heads_d, "tg": tg_d, "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
+                      "loss_host": torch.empty(4, dtype=torch.float32).pin_memory(),
+                      "off_host": torch.empty(B + 1, dtype=torch.int32).pin_memory(),
+                      "off_ready": torch.cuda.Event(), "rows_done": torch.cuda.Event(),
+                      "det_host": torch.empty(B * sum(G * G * 3 for G in grids), 6, dtype=torch.float32).pin_memory()})
+    if label_sets is None:
+        h2d = tensor_bytes(host_sets[0][0]) + tensor_bytes(host_sets[0][1])
+    else:
+        h2d = tensor_bytes(host_sets[0][0]) + tensor_bytes(list(label_sets[0]))
     d2h_acc = []
 
-    def e2e_step(i):
-        h_heads, h_tg = host_sets[i % n_sets]
-        preds = [h.to(dev, non_blocking=True).requires_grad_(True) for h in h_heads]
-        tgts = [t.to(dev, non_blocking=True) for t in h_tg]
-        if group is None:
-            total, bbox, obj, cls = yb.yolo_loss_multiscale(preds, tgts, anchors, nc)
-        else:
-            total, bbox, obj, cls = ops._loss_common(preds, tgts, anchors, nc, weights, group=group)
-        total.backward()
-        loss_host.copy_(torch.stack([total.detach(), bbox.detach(), obj.detach(), cls.detach()]), non_blocking=True)
-        det = yb.detect_batch([p.detach() for p in preds], anchors, img, nc, args.conf, args.iou)
-        rows_d, offsets = yb.pack_detections(det)
-        off_host.copy_(offsets, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        n = int(off_host[-1])
-        det_host[:n].copy_(rows_d[:n], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        d2h_acc.append(16 + off_host.numel() * 4 + n * 24)
-        return preds
+    def enqueue_h2d(i):
+        sl = slots[i % n_slots]
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(sl["free"])          # the slot's previous user has finished computing
+            for d, h in zip(sl["heads"], host_sets[i % n_sets][0]):
+                d.copy_(h, non_blocking=True)
+            if label_sets is None:
+                for d, h in zip(sl["tg"], host_sets[i % n_sets][1]):
+                    d.copy_(h, non_blocking=True)
+            else:
+                lab, n_gt, lb = label_sets[i % n_sets]
+                sl["tg"].labels.copy_(lab, non_blocking=True)
+                sl["tg"].n_gt.copy_(n_gt, non_blocking=True)
+                sl["tg"].letterbox.copy_(lb, non_blocking=True)
+            sl["ready"].record(h2d_stream)
 
-    for i in range(max(3, args.warmup)):
-        e2e_step(i)
+    def compute(i):
+        sl = slots[i % n_slots]
+        comp.wait_event(sl["ready"])
+        comp.wait_event(sl["rows_done"])               # the slot's host result buffers are free again
+        preds = [h.detach().requires_grad_(True) for h in sl["heads"]]
+        if label_sets is not None:
+            total, bbox, obj, cls = ops.yolo_loss_multiscale_labels(preds, sl["tg"], anchors, nc, img, group=group)
+        elif group is None:
+            total, bbox, obj, cls = yb.yolo_loss_multiscale(preds, sl["tg"], anchors, nc)
+        else:
+            total, bbox, obj, cls = ops._loss_common(preds, sl["tg"], anchors, nc, weights, group=group)
+        total.backward()
+        sl["loss_host"].copy_(torch.stack([total.detach(), bbox.detach(), obj.detach(), cls.detach()]),
+                              non_blocking=True)
+        det = yb.detect_batch(sl["heads"], anchors, img, nc, args.conf, args.iou)
+        rows_d, offsets = yb.pack_detections(det)
+        sl["off_host"].copy_(offsets, non_blocking=True)
+        sl["free"].record(comp)
+        sl["off_ready"].record(comp)
+        sl["rows_d"], sl["grads"] = rows_d, [p.grad for p in preds]
+
+    def collect(i):
+        sl = slots[i % n_slots]
+        sl["off_ready"].synchronize()                  # host needs the row count; step i+1's H2D is in flight
+        n = int(sl["off_host"][-1])
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(sl["off_ready"])
+            sl["det_host"][:n].copy_(sl["rows_d"][:n], non_blocking=True)
+            sl["rows_d"].record_stream(d2h_stream)
+            sl["rows_done"].record(d2h_stream)
+        d2h_acc.append(16 + sl["off_host"].numel() * 4 + n * 24)
+
+    def run(n_steps):
+        enqueue_h2d(0)
+        for i in range(n_steps):
+            if i + 1 < n_steps:
+                enqueue_h2d(i + 1)
+            compute(i)
+            collect(i)
+        d2h_stream.synchronize()
+        comp.synchronize()
+
+    run(max(3, args.warmup))
     d2h_acc.clear()
     barrier()
     t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    g1.record()
+    run(args.steps)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)) / args.steps
+    e2e_ms = max_over_ranks(wall_ms) / args.steps
+    api = ("yolo_loss_multiscale_labels(heads, packed labels)" if label_sets is not None
+           else "yolo_loss_multiscale(heads, dense targets)")
     return {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(np.mean(d2h_acc)),
-            "api": "yolo_loss_multiscale(...).backward() + detect_batch + pack_detections, pinned host tensors"}
+            "api": api + ".backward() + detect_batch + pack_detections; pinned host tensors, H2D / compute / D2H "
+                   "pipelined over 2 input slots, timed by host wall clock around all steps"}
 
 
 def run_torch_gpu_reference(args, dev, sample_images):

@@ -110,6 +110,21 @@ int yb_loss_finalize(const yb_loss_desc* d, const double* partials /* S*4, reduc
                      float* out4, float* per_scale /* S*3, nullable */,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* f-4: the same stage 1 fed by label lists instead of dense targets — the label loop of
+ * YOLODataset.__getitem__ (train.py:147-205, as yb_build_targets) runs on the device and hands the
+ * loss a sparse form of its result: per-scale lists of the assigned rows, their 32-byte target rows
+ * and a 1-bit-per-row positive map.  Neither the dense targets (3 tensors the size of the heads) nor
+ * their host->device copy (train.py:900-902) exist on this path; d->tgt[] is ignored.
+ *   labels (B,max_gt,5) fp64, n_gt (B) int32, letterbox (B,5) fp64, anchors_all (S,A,2) fp32,
+ *   assign_img_size = the dataset's img_size (:159-167); status as in yb_build_targets.
+ * Results equal yb_loss_partials on the dense targets yb_build_targets would have produced.
+ * Stage 2 is yb_loss_finalize with the same workspace. */
+size_t yb_loss_sparse_workspace_bytes(const yb_loss_desc* d, int max_gt);
+int yb_loss_partials_sparse(const yb_loss_desc* d, const double* labels, const int* n_gt,
+                            const double* letterbox, const float* anchors_all, int max_gt,
+                            int assign_img_size, int* status, double* partials /* S*4 */,
+                            void* ws, size_t ws_bytes, void* stream);
+
 /* x[i] *= *factor for i < n, skipped entirely (no memory traffic) when *factor == 1.0f.
  * Used by the autograd wrapper to apply the upstream gradient of `total` to the gradient the
  * fused kernel already produced (loss.backward() passes exactly 1.0).  factor is a device pointer. */
@@ -214,6 +229,20 @@ int yb_nms_graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned
 int yb_pack_detections(const float* boxes, const float* scores, const int64_t* classes,
                        const int64_t* keep, const int* n_keep, int B, int cap, float* out,
                        int* offsets, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f-1  detection counting of eval_epoch                      train.py:993-1024, 928-958
+ *   For every row of every scale: p = sigmoid(pred obj), t = target obj (both compared with
+ *   conf_threshold in double, as `.item()` values are in the reference);
+ *     p > conf and t > conf : IoU(decoded pred xywh, target xywh; compute_box_iou, eps 1e-6, fp32)
+ *                              > (float)iou_threshold ? TP : FP
+ *     p > conf only         : FP          t > conf only : FN
+ *   d->img_size is the decode img_size (the reference always uses its default 640 here, :993).
+ *   targets_host: HOST array of S device pointers, same layout as d->pred.
+ *   counts3 (device, int64[3]) += {TP, FP, FN}: the caller zeroes it once per epoch.
+ * ---------------------------------------------------------------------------------------- */
+int yb_eval_counts(const yb_heads_desc* d, const float* const* targets_host, double conf_threshold,
+                   double iou_threshold, long long* counts3, void* stream);
 
 /* Per-launch CUDA-event timing for bench.py: when enabled every kernel launch of the library is
  * bracketed by two events on its stream; yb_timing_collect synchronises them, writes

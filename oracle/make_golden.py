@@ -269,6 +269,72 @@ def golden_model_heads():
     np.savez_compressed(os.path.join(OUT, "model_heads.npz"), **out)
 
 
+class FakeEvalModel:
+    """Stands in for YOLO inside the reference's eval_epoch(): preset heads per batch."""
+
+    def __init__(self, batches, img, anchors):
+        self.batches, self.k = batches, 0
+        self.anchors = anchors
+        self.grid_size_p3, self.grid_size_p4, self.grid_size_p5 = img // 8, img // 16, img // 32
+
+    def eval(self):
+        return self
+
+    def __call__(self, imgs):
+        heads = self.batches[self.k]
+        self.k += 1
+        return heads
+
+
+def heads_near_targets(tgts, anchors, nc, seed, hit=0.7, jitter=0.35):
+    """randn heads; on a share of the positive cells the logits are set so that the decoded box
+    lands near the target (objectness high): gives eval_epoch true positives, misses and misfits."""
+    heads = []
+    rng = np.random.default_rng(seed)
+    for s, t in enumerate(tgts):
+        B, G = t.shape[0], t.shape[1]
+        h = torch.randn(t.shape, generator=gen(seed * 10 + s))
+        pos = (t[..., 4] > 0.5).nonzero()
+        for b, gy, gx, a in pos.tolist():
+            if rng.uniform() > hit:
+                continue
+            xc, yc, w, hh = [float(v) for v in t[b, gy, gx, a, 0:4]]
+            j = lambda: float(np.exp(rng.normal(0, jitter)))
+            sx = min(max((xc * G - gx + 0.5) / 2 + rng.normal(0, 0.05), 0.02), 0.98)
+            sy = min(max((yc * G - gy + 0.5) / 2 + rng.normal(0, 0.05), 0.02), 0.98)
+            sw = min(max(np.sqrt(w * j() * 640.0 / float(anchors[s][a, 0])) / 2, 0.02), 0.98)
+            sh = min(max(np.sqrt(hh * j() * 640.0 / float(anchors[s][a, 1])) / 2, 0.02), 0.98)
+            logit = lambda p: float(np.log(p / (1 - p)))
+            h[b, gy, gx, a, 0:4] = torch.tensor([logit(sx), logit(sy), logit(sw), logit(sh)])
+            h[b, gy, gx, a, 4] = float(rng.normal(1.5, 1.5))
+        heads.append(h)
+    return heads
+
+
+def golden_eval():
+    """The reference's own eval_epoch() (train.py:960-1032) on preset heads and reference-assigned
+    targets: loss + the python TP/FP/FN loop -> (avg_loss, precision, recall, f1)."""
+    out = {}
+    rng = np.random.default_rng(91)
+    for name, img, nc, B, nb, conf, iou in [("e640", 640, 1, 2, 1, 0.5, 0.5), ("e320", 320, 3, 2, 2, 0.3, 0.4)]:
+        batches, loader = [], []
+        for k in range(nb):
+            tgts = dense_targets_from_labels(B, img, nc, rng, 14)
+            heads = heads_near_targets(tgts, anchors3(), nc, 900 + k + img)
+            batches.append(heads)
+            imgs = torch.zeros(B, 3, 8, 8)
+            loader.append((imgs, [[tgts[s][b] for s in range(3)] for b in range(B)]))
+            for s in range(3):
+                out[f"{name}_b{k}_head{s}"] = heads[s].numpy()
+                out[f"{name}_b{k}_tgt{s}"] = tgts[s].numpy()
+        model = FakeEvalModel(batches, img, anchors3())
+        res = ref.eval_epoch(model, loader, torch.device("cpu"), num_classes=nc, iou_threshold=iou, conf_threshold=conf)
+        out[f"{name}_cfg"] = np.array([img, nc, B, nb, conf, iou], dtype=np.float64)
+        out[f"{name}_result"] = np.array([float(r) for r in res], dtype=np.float64)
+        print(name, "eval_epoch ->", res)
+    np.savez_compressed(os.path.join(OUT, "eval.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -279,5 +345,6 @@ if __name__ == "__main__":
     golden_predict()
     golden_nms()
     golden_model_heads()
+    golden_eval()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -18,7 +18,7 @@ import torch
 
 __all__ = [
     "decode", "ciou", "single_scale_loss", "multiscale_loss", "shape_iou", "assign_targets",
-    "candidates", "nms_indices", "batched_nms_indices", "detect", "python_list_nms", "corner_iou",
+    "eval_counts", "eval_metrics", "candidates", "nms_indices", "batched_nms_indices", "detect", "python_list_nms", "corner_iou",
     "default_anchors", "MULTISCALE_OBJ_WEIGHTS",
 ]
 
@@ -183,6 +183,44 @@ def candidates(preds, anchors_list, img_size, num_classes=1, conf=0.5, scale=1.0
     if not boxes:
         return torch.zeros(0, 4), torch.zeros(0), torch.zeros(0, dtype=torch.long)
     return torch.cat(boxes), torch.cat(scores), torch.cat(classes)            # :1227-1229
+
+
+# ---------------------------------------------------------------------------------------------
+# eval_epoch's detection counting — train.py:993-1024 with compute_box_iou :928-958
+# ---------------------------------------------------------------------------------------------
+def eval_counts(preds, targets, anchors_list, conf_threshold=0.5, iou_threshold=0.5):
+    """(TP, FP, FN) over all scales/images/cells/anchors, as the reference's 4-deep python loop counts
+    them.  `.item()` turns fp32 values into python floats, so the confidence tests run in double;
+    `iou > iou_threshold` compares an fp32 tensor with a python scalar, i.e. in fp32."""
+    tp = fp = fn = 0
+    for pred, tgt, anchors in zip(preds, targets, anchors_list):
+        dec = decode(pred, anchors)                                    # :993 (img_size defaults to 640)
+        p_obj = torch.sigmoid(pred[..., 4]).double()                   # :997, :1003
+        t_obj = tgt[..., 4].double()                                   # :1004
+        p_on, t_on = p_obj > conf_threshold, t_obj > conf_threshold
+        both = p_on & t_on
+        if bool(both.any()):
+            a, b = dec[..., 0:4][both], tgt[..., 0:4][both]            # :1008-1010
+            a_x1, a_y1, a_x2, a_y2 = a[:, 0] - a[:, 2] / 2, a[:, 1] - a[:, 3] / 2, a[:, 0] + a[:, 2] / 2, a[:, 1] + a[:, 3] / 2
+            b_x1, b_y1, b_x2, b_y2 = b[:, 0] - b[:, 2] / 2, b[:, 1] - b[:, 3] / 2, b[:, 0] + b[:, 2] / 2, b[:, 1] + b[:, 3] / 2
+            inter = torch.clamp(torch.min(a_x2, b_x2) - torch.max(a_x1, b_x1), min=0) * \
+                torch.clamp(torch.min(a_y2, b_y2) - torch.max(a_y1, b_y1), min=0)          # :945-950
+            union = (a_x2 - a_x1) * (a_y2 - a_y1) + (b_x2 - b_x1) * (b_y2 - b_y1) - inter  # :953-955
+            iou = inter / (union + 1e-6)                                                   # :957
+            hit = int((iou > iou_threshold).sum())                                         # :1012
+            tp += hit
+            fp += int(both.sum()) - hit                                                    # :1015
+        fp += int((p_on & ~t_on).sum())                                                    # :1016-1018
+        fn += int((~p_on & t_on).sum())                                                    # :1019-1021
+    return tp, fp, fn
+
+
+def eval_metrics(tp, fp, fn):
+    """precision, recall, F1 in percent — train.py:1026-1032."""
+    precision = tp / (tp + fp) if (tp + fp) > 0 else 0
+    recall = tp / (tp + fn) if (tp + fn) > 0 else 0
+    f1 = 2 * precision * recall / (precision + recall) if (precision + recall) > 0 else 0
+    return precision * 100, recall * 100, f1 * 100
 
 
 # ---------------------------------------------------------------------------------------------

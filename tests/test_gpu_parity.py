@@ -245,6 +245,85 @@ def test_loss_two_rank_emulation_on_one_gpu(yb):
             close(grads[s], full_g[s][lo:hi], rtol=1e-5, atol=1e-9)
 
 
+# ---- sparse-target loss ------------------------------------------------------------
+def _random_labels(rng, B, nc, max_n, lo=0.05, hi=0.95):
+    labels = []
+    for _ in range(B):
+        n = int(rng.integers(0, max_n + 1))
+        lab = np.zeros((n, 5))
+        lab[:, 0] = rng.integers(0, max(nc, 1), n)
+        lab[:, 1:3] = rng.uniform(lo, hi, (n, 2))
+        lab[:, 3:5] = np.exp(rng.uniform(np.log(0.01), np.log(0.6), (n, 2)))
+        labels.append(lab)
+    return labels
+
+
+@pytest.mark.parametrize("B,nc,grids,img,max_n", [(8, 1, (80, 40, 20), 640, 50), (4, 3, (16, 8, 4), 128, 12),
+                                                    (3, 80, (20, 10, 5), 160, 30), (2, 1, (13, 6, 3), 104, 0)])
+def test_sparse_label_loss_equals_dense_and_oracle(yb, B, nc, grids, img, max_n):
+    """yolo_loss_multiscale_labels (device-side assignment, sparse targets) == the dense call on
+    yb.build_targets' tensors == the oracle on the oracle's own assignment, values and gradients.
+    Duplicate cells (first ground truth wins) are forced by repeating labels."""
+    g = torch.Generator().manual_seed(100 + B + nc)
+    heads = [torch.randn(B, G, G, 3, 5 + nc, generator=g) for G in grids]
+    rng = np.random.default_rng(B * 7 + nc)
+    labels = _random_labels(rng, B, nc, max_n)
+    if max_n:
+        labels[0] = np.concatenate([labels[0], labels[0][:3] * np.array([1, 1, 1, 1.0001, 0.9999])])  # same cells
+    sp = [h.cuda().requires_grad_(True) for h in heads]
+    res_s = yb.yolo_loss_multiscale_labels(sp, labels, ANCH, nc, img)
+    res_s[0].backward()
+    tg = yb.build_targets(labels, ANCH, list(grids), nc, img)
+    dp = [h.cuda().requires_grad_(True) for h in heads]
+    res_d = yb.yolo_loss_multiscale(dp, tg, ANCH, nc)
+    res_d[0].backward()
+    for a, b in zip(res_s, res_d):
+        close(a, b, rtol=1e-6, atol=1e-7)
+    for p, q in zip(sp, dp):
+        close(p.grad, q.grad, rtol=1e-6, atol=1e-10)
+    ref_t = [R.assign_targets(l, ANCH, list(grids), nc, img) for l in labels]
+    ref_tg = [torch.from_numpy(np.stack([t[s] for t in ref_t])) for s in range(3)]
+    ref_p = [h.clone().requires_grad_(True) for h in heads]
+    ref = R.multiscale_loss(ref_p, ref_tg, ANCH, nc)
+    ref[0].backward()
+    for a, b in zip(res_s, ref):
+        close(a, float(b), atol=1e-7)
+    for p, q in zip(sp, ref_p):
+        grad_close(p.grad, q.grad)
+
+
+def test_sparse_label_loss_packed_letterbox_and_errors(yb):
+    """PackedLabels input with a real letterbox; a label outside the grid is reported like the
+    reference's IndexError; no_grad and upstream-gradient paths work."""
+    from yolo_from_scratch_b200 import ops
+    nc, img, grids, B = 2, 256, (32, 16, 8), 3
+    g = torch.Generator().manual_seed(9)
+    heads = [torch.randn(B, G, G, 3, 5 + nc, generator=g) for G in grids]
+    labels = _random_labels(np.random.default_rng(3), B, nc, 9, 0.2, 0.8)
+    lb = [(500.0, 375.0, 0.512, 32.0, 0.0), (256.0, 256.0, 1.0, 0.0, 0.0), (300.0, 600.0, 256 / 600, 0.0, 64.0)]
+    packed = ops.pack_labels(labels, img, lb)
+    sp = [h.cuda().requires_grad_(True) for h in heads]
+    res = yb.yolo_loss_multiscale_labels(sp, packed, ANCH, nc, img)
+    (res[0] * 3.0).backward()
+    packed.check()
+    tg = yb.build_targets(labels, ANCH, list(grids), nc, img, letterbox=lb)
+    dp = [h.cuda().requires_grad_(True) for h in heads]
+    res_d = yb.yolo_loss_multiscale(dp, tg, ANCH, nc)
+    (res_d[0] * 3.0).backward()
+    for a, b in zip(res, res_d):
+        close(a, b, rtol=1e-6, atol=1e-7)
+    for p, q in zip(sp, dp):
+        close(p.grad, q.grad, rtol=1e-6, atol=1e-10)
+    with torch.no_grad():
+        res_n = yb.yolo_loss_multiscale_labels([h.cuda() for h in heads], packed, ANCH, nc, img)
+    close(res_n[0], res[0], rtol=1e-6, atol=1e-7)
+    bad = [np.array([[0, -1.5, 0.5, 0.1, 0.1]])] + labels[1:]  # int(-1.5*G) < -G: IndexError in the reference
+    pk = ops.pack_labels(bad, img)
+    yb.yolo_loss_multiscale_labels([h.cuda() for h in heads], pk, ANCH, nc, img)
+    with pytest.raises(IndexError):
+        pk.check()
+
+
 # ---- target assignment ------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["a", "b", "c", "d", "e", "f", "g"])
 def test_build_targets_golden_bitexact(yb, golden, name):

@@ -9,10 +9,12 @@ from . import _lib
 from .ops import (batched_nms, batched_nms_padded, build_targets, ciou_loss, compute_anchor_iou,
                   decode_predictions, detect_batch, detections_to_lists, filter_candidates,
                   loss_forward_backward, nms, nms_retry_overflow, pack_detections,
-                  NMS_GRAPH, NMS_BITMASK, yolo_loss, yolo_loss_multiscale)
+                  NMS_GRAPH, NMS_BITMASK, PackedLabels, pack_labels, pack_labels_host, yolo_loss,
+                  yolo_loss_multiscale, yolo_loss_multiscale_labels)
 
 __all__ = [
     "decode_predictions", "ciou_loss", "yolo_loss", "yolo_loss_multiscale", "compute_anchor_iou",
     "build_targets", "filter_candidates", "nms", "batched_nms", "batched_nms_padded", "detect_batch",
-    "detections_to_lists", "pack_detections", "loss_forward_backward",
+    "detections_to_lists", "pack_detections", "loss_forward_backward", "yolo_loss_multiscale_labels",
+    "PackedLabels", "pack_labels", "pack_labels_host",
 ]

@@ -52,6 +52,9 @@ SIGNATURES = {
     "yb_loss_workspace_bytes": (c_size_t, [POINTER(LossDesc)]),
     "yb_loss_partials": (c_int, [POINTER(LossDesc), c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_loss_finalize": (c_int, [POINTER(LossDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yb_loss_sparse_workspace_bytes": (c_size_t, [POINTER(LossDesc), c_int]),
+    "yb_loss_partials_sparse": (c_int, [POINTER(LossDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_scale_inplace": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
     "yb_anchor_iou": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "yb_build_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int,
@@ -65,6 +68,7 @@ SIGNATURES = {
     "yb_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_longlong, c_int,
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_nms_graph_stats": (c_int, [c_void_p, c_size_t, c_int, c_int, POINTER(c_ulonglong), POINTER(c_ulonglong), c_void_p]),
+    "yb_eval_counts": (c_int, [POINTER(HeadsDesc), POINTER(c_void_p), c_double, c_double, c_void_p, c_void_p]),
     "yb_pack_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),
 }

@@ -154,6 +154,7 @@ struct LossScale {
     const float* tgt;
     const float* anchors;
     float* grad;
+    const uint32_t* bits; // sparse targets: 1 bit per row (positive), else null
     uint32_t rows;        // B*H*W*A (local)
     uint32_t tile_begin;  // first global tile index of this scale
     uint32_t list_begin;  // offset of this scale's positive list in ws
@@ -172,6 +173,8 @@ struct LossArgs {
     LossScale sc[YB_MAX_SCALES];
     int* pos_count;      // [YB_MAX_SCALES] in ws
     uint32_t* pos_list;  // ws
+    const uint32_t* pos_ent;     // sparse targets: entry id of each listed row
+    const SparseEntry* entries;  // sparse targets: target rows
     double* partials;    // S*4: {sum(1-ciou), n_pos, sum bce_obj, sum bce_cls}
 };
 
@@ -180,6 +183,7 @@ struct LossWs {
     int pad[12];
 };
 
+template <bool SPARSE>
 __global__ void __launch_bounds__(kTileRows) loss_main_kernel(const LossArgs a) {
     __shared__ float s_dobj[kTileRows];
     __shared__ float s_warp[kTileRows / 32];
@@ -204,13 +208,19 @@ __global__ void __launch_bounds__(kTileRows) loss_main_kernel(const LossArgs a) 
         if (threadIdx.x < nrows) {
             const size_t off = (size_t)(row0 + threadIdx.x) * a.row + 4;
             const float x = __ldg(L.pred + off);
-            const float t = __ldg(L.tgt + off);
+            float t;
+            if (SPARSE) {
+                const uint32_t r = row0 + threadIdx.x;
+                t = ((__ldg(L.bits + (r >> 5)) >> (r & 31)) & 1u) ? 1.0f : 0.0f;
+            } else {
+                t = __ldg(L.tgt + off);
+            }
             bce = bce_logits_ref(x, t);
             s_dobj[threadIdx.x] = (sigmoidf_ref(x) - t) * L.obj_scale;
             pos = t > 0.5f;
         }
         // positives: warp-aggregated append
-        const unsigned bal = __ballot_sync(0xffffffffu, pos);
+        const unsigned bal = SPARSE ? 0u : __ballot_sync(0xffffffffu, pos);  // sparse: lists come from the assignment
         if (bal) {
             int base = 0;
             if (lane == 0) base = atomicAdd(a.pos_count + s, __popc(bal));
@@ -261,6 +271,7 @@ __global__ void __launch_bounds__(kTileRows) loss_main_kernel(const LossArgs a) 
 }
 
 // one warp per positive row
+template <bool SPARSE>
 __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
     const int lane = threadIdx.x & 31;
     const int warps_per_cta = blockDim.x >> 5;
@@ -273,7 +284,9 @@ __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
         for (uint32_t k = gwarp; k < P; k += nwarps) {
             const uint32_t r = a.pos_list[L.list_begin + k];
             const float* x = L.pred + (size_t)r * a.row;
-            const float* t = L.tgt + (size_t)r * a.row;
+            const float* t = SPARSE ? nullptr : L.tgt + (size_t)r * a.row;
+            SparseEntry ent = {0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0};
+            if (SPARSE) ent = a.entries[a.pos_ent[L.list_begin + k]];
             uint32_t cell, an, gy_b, gx, gy, bi;
             L.d_A.divmod(r, cell, an);
             L.d_W.divmod(cell, gy_b, gx);
@@ -282,13 +295,15 @@ __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
             const float xr[4] = {x[0], x[1], x[2], x[3]};
             const float p[4] = {decode_xy(xr[0], (float)gx, L.inv_w), decode_xy(xr[1], (float)gy, L.inv_h),
                                 decode_wh(xr[2], aw, a.inv_img), decode_wh(xr[3], ah, a.inv_img)};
-            const float tb[4] = {t[0], t[1], t[2], t[3]};
+            const float tb[4] = {SPARSE ? ent.x : t[0], SPARSE ? ent.y : t[1], SPARSE ? ent.w : t[2],
+                                 SPARSE ? ent.h : t[3]};
             float gp[4];
             const float l = ciou_pair<true>(p, tb, a.eps, gp, nullptr);
             // class BCE, lanes stride over classes
             float cls = 0.0f;
             for (int c = lane; c < a.nc; c += 32) {
-                const float xc = x[5 + c], tc = t[5 + c];
+                const float xc = x[5 + c];
+                const float tc = SPARSE ? (c == ent.cls ? 1.0f : 0.0f) : t[5 + c];
                 cls += bce_logits_ref(xc, tc);
                 if (L.grad) L.grad[(size_t)r * a.row + 5 + c] = sigmoidf_ref(xc) - tc;
             }
@@ -385,7 +400,7 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, long 
 }
 
 // ---- host side ----------------------------------------------------------------------------
-static int loss_validate(const yb_loss_desc* d, bool need_ptrs) {
+static int loss_validate(const yb_loss_desc* d, bool need_ptrs, bool sparse = false) {
     YB_CHECK_ARG(d, "loss: null descriptor");
     YB_CHECK_ARG(d->S >= 1 && d->S <= YB_MAX_SCALES, "loss: S=%d out of range", d->S);
     YB_CHECK_ARG(d->B >= 0 && d->A > 0 && d->A <= YB_MAX_ANCHORS && d->nc >= 0, "loss: bad B/A/nc");
@@ -397,8 +412,8 @@ static int loss_validate(const yb_loss_desc* d, bool need_ptrs) {
         YB_CHECK_ARG(n < (1ull << 32), "loss: scale %d too large", s);
         tot += (unsigned long long)d->B * d->H[s] * d->W[s] * d->A;
         if (need_ptrs && d->B > 0) {
-            YB_CHECK_ARG(d->pred[s] && d->tgt[s] && d->anchors[s], "loss: null tensor at scale %d", s);
-            YB_CHECK_ARG(aligned16(d->pred[s]) && aligned16(d->tgt[s]) && aligned16(d->grad[s]),
+            YB_CHECK_ARG(d->pred[s] && (sparse || d->tgt[s]) && d->anchors[s], "loss: null tensor at scale %d", s);
+            YB_CHECK_ARG(aligned16(d->pred[s]) && (sparse || aligned16(d->tgt[s])) && aligned16(d->grad[s]),
                          "loss: tensors must be 16-byte aligned");
         }
     }
@@ -417,6 +432,7 @@ static void loss_fill_args(const yb_loss_desc* d, void* ws, LossArgs& a) {
     for (int s = 0; s < d->S; ++s) {
         LossScale& L = a.sc[s];
         L.pred = d->pred[s]; L.tgt = d->tgt[s]; L.anchors = d->anchors[s]; L.grad = d->grad[s];
+        L.bits = nullptr;
         L.rows = (uint32_t)((unsigned long long)d->B * d->H[s] * d->W[s] * d->A);
         L.tile_begin = tile; L.list_begin = list;
         tile += (L.rows + kTileRows - 1) / kTileRows;
@@ -428,6 +444,27 @@ static void loss_fill_args(const yb_loss_desc* d, void* ws, LossArgs& a) {
         L.d_A = FastDiv(d->A); L.d_W = FastDiv(d->W[s]); L.d_H = FastDiv(d->H[s]);
     }
     a.n_tiles = tile;
+    a.pos_ent = nullptr;
+    a.entries = nullptr;
+}
+
+// sparse-target workspace: [dense-layout workspace][pos_ent: rows u32][entries][bits]
+struct SparseLayout { size_t pos_ent, entries, bits, total; uint32_t bits_begin[YB_MAX_SCALES]; };
+static SparseLayout sparse_layout(const yb_loss_desc* d, int max_gt) {
+    SparseLayout L;
+    size_t rows = 0, words = 0;
+    for (int s = 0; s < d->S; ++s) {
+        const size_t r = (size_t)d->B * d->H[s] * d->W[s] * d->A;
+        L.bits_begin[s] = (uint32_t)words;
+        words += (r + 31) / 32;
+        rows += r;
+    }
+    size_t o = (sizeof(LossWs) + rows * sizeof(uint32_t) + 15) / 16 * 16;
+    L.pos_ent = o; o = (o + rows * sizeof(uint32_t) + 15) / 16 * 16;
+    L.entries = o; o += (size_t)d->B * (max_gt > 0 ? max_gt : 1) * sizeof(SparseEntry);
+    L.bits = o; o += (words + 4) * sizeof(uint32_t);
+    L.total = o + 16;
+    return L;
 }
 
 }  // namespace yb
@@ -485,8 +522,63 @@ extern "C" int yb_loss_partials(const yb_loss_desc* d, double* partials, void* w
     if (a.n_tiles == 0) return 0;
     const int sms = sm_count();
     int blocks = (int)(a.n_tiles < (uint32_t)(sms * 8) ? a.n_tiles : (uint32_t)(sms * 8));
-    YB_LAUNCH("loss_main_kernel", st, loss_main_kernel<<<blocks, kTileRows, 0, st>>>(a));
-    YB_LAUNCH("loss_positive_kernel", st, loss_positive_kernel<<<sms * 2, 256, 0, st>>>(a));
+    YB_LAUNCH("loss_main_kernel", st, loss_main_kernel<false><<<blocks, kTileRows, 0, st>>>(a));
+    YB_LAUNCH("loss_positive_kernel", st, loss_positive_kernel<false><<<sms * 2, 256, 0, st>>>(a));
+    return 0;
+}
+
+extern "C" size_t yb_loss_sparse_workspace_bytes(const yb_loss_desc* d, int max_gt) {
+    if (!d || d->S < 1 || d->S > YB_MAX_SCALES || max_gt < 0) return 0;
+    return yb::sparse_layout(d, max_gt).total;
+}
+
+extern "C" int yb_loss_partials_sparse(const yb_loss_desc* d, const double* labels, const int* n_gt,
+                                       const double* letterbox, const float* anchors_all, int max_gt,
+                                       int assign_img_size, int* status, double* partials, void* ws,
+                                       size_t ws_bytes, void* stream) {
+    using namespace yb;
+    int rc = loss_validate(d, true, true);
+    if (rc) return rc;
+    YB_CHECK_ARG(partials && ws && n_gt && letterbox && anchors_all && max_gt >= 0 && (max_gt == 0 || labels) &&
+                     assign_img_size > 0,
+                 "loss(sparse): bad arguments");
+    const SparseLayout SL = sparse_layout(d, max_gt);
+    if (ws_bytes < SL.total) {
+        set_error("loss(sparse): workspace %zu < %zu", ws_bytes, SL.total);
+        return YB_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    LossArgs a;
+    loss_fill_args(d, ws, a);
+    a.partials = partials;
+    char* w = reinterpret_cast<char*>(ws);
+    SparseOut o;
+    o.entries = reinterpret_cast<SparseEntry*>(w + SL.entries);
+    o.bits = reinterpret_cast<uint32_t*>(w + SL.bits);
+    o.pos_count = a.pos_count;
+    o.pos_list = a.pos_list;
+    o.pos_ent = reinterpret_cast<uint32_t*>(w + SL.pos_ent);
+    int G[YB_MAX_SCALES];
+    for (int s = 0; s < d->S; ++s) {
+        YB_CHECK_ARG(d->H[s] == d->W[s], "loss(sparse): the reference assigns on square grids (scale %d)", s);
+        G[s] = d->H[s];
+        o.bits_begin[s] = SL.bits_begin[s];
+        o.list_begin[s] = a.sc[s].list_begin;
+        a.sc[s].bits = o.bits + SL.bits_begin[s];
+    }
+    a.pos_ent = o.pos_ent;
+    a.entries = o.entries;
+    YB_CUDA(cudaMemsetAsync(ws, 0, sizeof(LossWs), st));
+    YB_CUDA(cudaMemsetAsync(o.bits, 0, SL.total - 16 - SL.bits, st));
+    YB_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * 4 * d->S, st));
+    if (a.n_tiles == 0) return 0;
+    rc = launch_assign_sparse(labels, n_gt, letterbox, anchors_all, d->B, max_gt, d->S, G, d->A, d->nc, assign_img_size,
+                              status, o, st);
+    if (rc) return rc;
+    const int sms = sm_count();
+    int blocks = (int)(a.n_tiles < (uint32_t)(sms * 8) ? a.n_tiles : (uint32_t)(sms * 8));
+    YB_LAUNCH("loss_main_kernel", st, loss_main_kernel<true><<<blocks, kTileRows, 0, st>>>(a));
+    YB_LAUNCH("loss_positive_kernel", st, loss_positive_kernel<true><<<sms * 2, 256, 0, st>>>(a));
     return 0;
 }
 

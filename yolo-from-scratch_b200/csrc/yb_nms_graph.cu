@@ -79,6 +79,7 @@ __device__ __forceinline__ u32 spread8(u32 v) {  // 8 bits -> even bit positions
     return v;
 }
 
+template <int NT>
 __device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float* s32, int lane, int warp) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -89,16 +90,29 @@ __device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float
     if (lane == 0) s32[warp] = v;
     __syncthreads();
     float r = s32[0];
-    for (int w = 1; w < 32; ++w) r = is_max ? fmaxf(r, s32[w]) : fminf(r, s32[w]);
+    for (int w = 1; w < NT / 32; ++w) r = is_max ? fmaxf(r, s32[w]) : fminf(r, s32[w]);
     return r;
 }
 
+// spatial sort key: (class | area octave pair | Morton(centre))
+__device__ __forceinline__ u32 spatial_key(const float4 q, const int64_t* classes, int i, float cmin, float qs) {
+    const float area = (q.z - q.x) * (q.w - q.y);
+    const u32 bucket = (__float_as_uint(area) >> 24) & 0x7fu;
+    const float fx = fminf(fmaxf(((q.x + q.z) * 0.5f - cmin) * qs, 0.0f), 255.0f);
+    const float fy = fminf(fmaxf(((q.y + q.w) * 0.5f - cmin) * qs, 0.0f), 255.0f);
+    const u32 mort = spread8((u32)fx) | (spread8((u32)fy) << 1);
+    const u32 c = classes ? ((u32)classes[i] & 0x1ffu) : 0u;
+    return (c << 23) | (bucket << 16) | mort;
+}
+
 // ------------------------------------------------------------------------------------------------
-// sort: two independent CTAs per image (blockIdx.y = 0: score order, 1: spatial order)
+// sort: two independent CTAs per image (blockIdx.y = 0: score order, 1: spatial order).
+// SMEM = true: shared-memory blocked sort (cap <= kS16MaxM, 512 threads); false: warp-ballot sort
+// through global ping-pong buffers (any cap, 1024 threads).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSortThreads) graph_sort_kernel(const GArgs a) {
-    __shared__ u32 s_hist[32 * 256];
-    __shared__ u32 s_tot[256];
+template <int NT, bool SMEM>
+__global__ void __launch_bounds__(NT) graph_sort_kernel(const GArgs a) {
+    extern __shared__ __align__(16) u32 s_dyn[];  // SMEM: s16_smem_bytes(cap); else 32*256 + 256 words
     __shared__ float s_f[32];
     __shared__ int s_flag[32];
     __shared__ int s_maxcls[32];
@@ -123,16 +137,25 @@ __global__ void __launch_bounds__(kSortThreads) graph_sort_kernel(const GArgs a)
     if (blockIdx.y == 0) {
         // ---- stable descending score sort: order[r] = original index, rinv[index] = r ---------------
         const float* scores = a.scores + off;
-        u32 *ka = a.k0 + off, *va = a.v0 + off, *kb = a.k1 + off, *vb = a.v1 + off;
-        for (int i = tid; i < M; i += kSortThreads) { ka[i] = desc_key(scores[i]); va[i] = (u32)i; }
-        __syncthreads();
-        radix_sort(ka, va, kb, vb, M, 0, 32, s_hist, s_tot, &s_skip);
         u32* order = a.order + off;
         u32* rinv = a.rinv + off;
-        for (int r = tid; r < M; r += kSortThreads) {
-            const u32 idx = va[r];
-            order[r] = idx;
-            rinv[idx] = (u32)r;
+        if (SMEM) {
+            const u32* res = s16_sort(M, a.cap, [&](int i) { return desc_key(scores[i]); }, s_dyn);
+            for (int r = tid; r < M; r += NT) {
+                const u32 idx = res[r] >> 16;
+                order[r] = idx;
+                rinv[idx] = (u32)r;
+            }
+        } else {
+            u32 *ka = a.k0 + off, *va = a.v0 + off, *kb = a.k1 + off, *vb = a.v1 + off;
+            for (int i = tid; i < M; i += NT) { ka[i] = desc_key(scores[i]); va[i] = (u32)i; }
+            __syncthreads();
+            radix_sort(ka, va, kb, vb, M, 0, 32, s_dyn, s_dyn + 32 * 256, &s_skip);
+            for (int r = tid; r < M; r += NT) {
+                const u32 idx = va[r];
+                order[r] = idx;
+                rinv[idx] = (u32)r;
+            }
         }
         return;
     }
@@ -141,7 +164,7 @@ __global__ void __launch_bounds__(kSortThreads) graph_sort_kernel(const GArgs a)
     const int mode = !classes ? G_PLAIN : ((long long)M * 4 <= a.trick_max_numel ? G_TRICK : G_CLASS);
     float mx = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
     int bad = 0, maxcls = 0;
-    for (int i = tid; i < M; i += kSortThreads) {
+    for (int i = tid; i < M; i += NT) {
         const float4 q = boxes[i];
         mx = fmaxf(mx, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
         const bool nan = (q.x != q.x) || (q.y != q.y) || (q.z != q.z) || (q.w != q.w);
@@ -159,34 +182,32 @@ __global__ void __launch_bounds__(kSortThreads) graph_sort_kernel(const GArgs a)
     bad = __reduce_or_sync(0xffffffffu, bad);
     maxcls = __reduce_max_sync(0xffffffffu, maxcls);
     if (lane == 0) { s_flag[warp] = bad; s_maxcls[warp] = maxcls; }
-    mx = block_reduce_minmax(mx, true, s_f, lane, warp);
-    cmin = block_reduce_minmax(cmin, false, s_f, lane, warp);
-    cmax = block_reduce_minmax(cmax, true, s_f, lane, warp);
+    mx = block_reduce_minmax<NT>(mx, true, s_f, lane, warp);
+    cmin = block_reduce_minmax<NT>(cmin, false, s_f, lane, warp);
+    cmax = block_reduce_minmax<NT>(cmax, true, s_f, lane, warp);
     bad = 0; maxcls = 0;
-    for (int w = 0; w < 32; ++w) { bad |= s_flag[w]; maxcls = max(maxcls, s_maxcls[w]); }
+    for (int w = 0; w < NT / 32; ++w) { bad |= s_flag[w]; maxcls = max(maxcls, s_maxcls[w]); }
     float s_off = mx + 1.0f;                            // boxes.py:99
     if (bad & 4) s_off = __int_as_float(0x7fc00000);    // torch max propagates NaN
     if (mode == G_TRICK && !((float)maxcls * s_off + fabsf(mx) <= 1e17f)) bad |= 1;
     const bool exact = (bad & 1) || !a.thr_fast_ok;
 
-    // ---- spatial order: (class | area octave pair | Morton(centre)), stable by original index --------
-    u32 *ka = a.k2 + off, *va = a.v2 + off, *kb = a.srank + off, *vb = a.scls + off;  // scratch until the gather
+    // ---- spatial order, stable by original index -----------------------------------------------------
     const float qs = (cmax > cmin) ? 255.0f / (cmax - cmin) : 0.0f;
-    for (int i = tid; i < M; i += kSortThreads) {
-        const float4 q = boxes[i];
-        const float area = (q.z - q.x) * (q.w - q.y);
-        const u32 bucket = (__float_as_uint(area) >> 24) & 0x7fu;
-        const float fx = fminf(fmaxf(((q.x + q.z) * 0.5f - cmin) * qs, 0.0f), 255.0f);
-        const float fy = fminf(fmaxf(((q.y + q.w) * 0.5f - cmin) * qs, 0.0f), 255.0f);
-        const u32 mort = spread8((u32)fx) | (spread8((u32)fy) << 1);
-        const u32 c = classes ? ((u32)classes[i] & 0x1ffu) : 0u;
-        ka[i] = (c << 23) | (bucket << 16) | mort;
-        va[i] = (u32)i;
-    }
-    __syncthreads();
-    radix_sort(ka, va, kb, vb, M, 0, 32, s_hist, s_tot, &s_skip);
     u32* pos = a.pos + off;
-    for (int p = tid; p < M; p += kSortThreads) pos[p] = va[p];
+    if (SMEM) {
+        const u32* res = s16_sort(M, a.cap, [&](int i) { return spatial_key(boxes[i], classes, i, cmin, qs); }, s_dyn);
+        for (int p = tid; p < M; p += NT) pos[p] = res[p] >> 16;
+    } else {
+        u32 *ka = a.k2 + off, *va = a.v2 + off, *kb = a.srank + off, *vb = a.scls + off;  // scratch until the gather
+        for (int i = tid; i < M; i += NT) {
+            ka[i] = spatial_key(boxes[i], classes, i, cmin, qs);
+            va[i] = (u32)i;
+        }
+        __syncthreads();
+        radix_sort(ka, va, kb, vb, M, 0, 32, s_dyn, s_dyn + 32 * 256, &s_skip);
+        for (int p = tid; p < M; p += NT) pos[p] = va[p];
+    }
     if (tid == 0) {
         GImg o;
         o.M = M; o.mode = mode; o.exact = exact ? 1 : 0;
@@ -633,7 +654,17 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     a.edges_per_img = (ws_bytes - L.edges) / 8 / (size_t)B;
     a.keep = keep; a.n_keep = n_keep;
 
-    YB_LAUNCH("graph_sort_kernel", st, graph_sort_kernel<<<dim3(B, 2), kSortThreads, 0, st>>>(a));
+    if (cap <= kS16MaxM) {
+        const size_t sort_smem = s16_smem_bytes(cap);
+        YB_CUDA(cudaFuncSetAttribute(graph_sort_kernel<kS16Threads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sort_smem));
+        YB_LAUNCH("graph_sort_kernel", st,
+                  (graph_sort_kernel<kS16Threads, true><<<dim3(B, 2), kS16Threads, sort_smem, st>>>(a)));
+    } else {
+        const size_t sort_smem = (32 * 256 + 256) * sizeof(u32);
+        YB_LAUNCH("graph_sort_kernel", st,
+                  (graph_sort_kernel<kSortThreads, false><<<dim3(B, 2), kSortThreads, sort_smem, st>>>(a)));
+    }
     const dim3 ggrid((a.tcap + kGatherThreads / 32 - 1) / (kGatherThreads / 32), B);
     YB_LAUNCH("graph_gather_kernel", st, graph_gather_kernel<<<ggrid, kGatherThreads, 0, st>>>(a));
     const int ctas = sm_count() * 4;

@@ -136,4 +136,131 @@ __device__ inline void radix_sort(u32*& ka, u32*& va, u32*& kb, u32*& vb, int M,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shared-memory blocked LSD radix sort (graph NMS, images of up to kS16MaxM candidates).
+//
+// The warp-ballot sort above spends ~250 instructions per key and pass; a first blocked variant
+// with per-thread counters needed only ~20 but scattered every key to global memory and ran into
+// the L2's sector-transaction rate (ncu, round 1: 23 sectors per store request).  Here the data
+// never leave shared memory between passes: a 32-bit key is sorted as two 16-bit halves (LSD order:
+// low half first), each element is ONE u32 (half key | index << 16), so two ping-pong buffers of
+// 4*M bytes plus 16 x 512 u16 counters fit the SM's 227 KB for M <= 26,880.
+// Thread t owns the K consecutive elements [t*K, t*K+K); counter (bin, t) lives at cnt[bin*T + t];
+// an exclusive scan in bin-major, thread-minor order gives stable destinations; each thread then
+// walks its elements again and scatters within shared memory.  4-bit digits, 8 passes, passes whose
+// digit is uniform are skipped.
+// ------------------------------------------------------------------------------------------------
+constexpr int kS16Threads = 512;
+constexpr int kS16Bins = 16;
+constexpr int kS16MaxM = 26880;
+typedef unsigned short u16;
+
+__host__ __device__ inline size_t s16_smem_bytes(int cap) {
+    const size_t n = ((size_t)cap + 3) / 4 * 4;
+    return 2 * n * sizeof(u32) + (size_t)kS16Bins * kS16Threads * sizeof(u16) + 64 * sizeof(u32);
+}
+
+__device__ inline bool s16_pass(const u32* __restrict__ in, u32* __restrict__ out, int M, int shift, u16* cnt,
+                                u32* wsum /*[16] + 2 flags*/, int pass) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = (((M + kS16Threads - 1) / kS16Threads) + 3) & ~3;
+    const int beg = min(tid * K, M), end = min(beg + K, M);
+    u32* flag = wsum + 16 + (pass & 1);  // alternating slots: no reset/read race between passes
+#pragma unroll
+    for (int b = 0; b < kS16Bins; ++b) cnt[b * kS16Threads + tid] = 0;
+    if (tid == 0) *flag = 0u;
+    u16* mine = cnt + tid;
+    int i = beg;
+    for (; i + 4 <= end; i += 4) {
+        const uint4 x = *reinterpret_cast<const uint4*>(in + i);
+        mine[((x.x >> shift) & 15u) * kS16Threads] += 1;
+        mine[((x.y >> shift) & 15u) * kS16Threads] += 1;
+        mine[((x.z >> shift) & 15u) * kS16Threads] += 1;
+        mine[((x.w >> shift) & 15u) * kS16Threads] += 1;
+    }
+    for (; i < end; ++i) mine[((in[i] >> shift) & 15u) * kS16Threads] += 1;
+    __syncthreads();
+    // exclusive scan of the 16*512 u16 counters in linear order; thread t owns cnt[16t, 16t+16)
+    uint4* seg = reinterpret_cast<uint4*>(cnt) + tid * 2;
+    const uint4 c0 = seg[0], c1 = seg[1];
+    const u32 w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    u32 v[16];
+    u32 tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[2 * j] = tot; tot += w[j] & 0xffffu;
+        v[2 * j + 1] = tot; tot += w[j] >> 16;
+    }
+    u32 inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    u32 base = inc - tot;
+#pragma unroll
+    for (int k = 0; k < kS16Threads / 32; ++k)
+        if (k < warp) base += wsum[k];
+    u32 o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o8[j] = ((base + v[2 * j]) & 0xffffu) | ((base + v[2 * j + 1]) << 16);
+    seg[0] = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+    seg[1] = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+    __syncthreads();
+    if (tid < kS16Bins) {  // bin b holds every key <=> its start is 0 and the next bin starts at M
+        const u32 lo = cnt[tid * kS16Threads];
+        const u32 hi = tid == kS16Bins - 1 ? (u32)M : (u32)cnt[(tid + 1) * kS16Threads];
+        // a count of exactly 65536 cannot occur (M <= kS16MaxM)
+        if (hi - lo == (u32)M && lo == 0u) *flag = 1u;
+    }
+    __syncthreads();
+    if (*flag) return false;
+    i = beg;
+    for (; i + 4 <= end; i += 4) {
+        const uint4 x = *reinterpret_cast<const uint4*>(in + i);
+        u16* p;
+        u32 d;
+        p = mine + ((x.x >> shift) & 15u) * kS16Threads; d = *p; *p = (u16)(d + 1u); out[d] = x.x;
+        p = mine + ((x.y >> shift) & 15u) * kS16Threads; d = *p; *p = (u16)(d + 1u); out[d] = x.y;
+        p = mine + ((x.z >> shift) & 15u) * kS16Threads; d = *p; *p = (u16)(d + 1u); out[d] = x.z;
+        p = mine + ((x.w >> shift) & 15u) * kS16Threads; d = *p; *p = (u16)(d + 1u); out[d] = x.w;
+    }
+    for (; i < end; ++i) {
+        const u32 x = in[i];
+        u16* p = mine + ((x >> shift) & 15u) * kS16Threads;
+        const u32 d = *p;
+        *p = (u16)(d + 1u);
+        out[d] = x;
+    }
+    __syncthreads();
+    return true;
+}
+
+// Stable ascending sort of the indices 0..M-1 by key(i) (32 bits), entirely in shared memory.
+// `key` is evaluated twice per element (low half at the start, high half gathered by index after the
+// first four passes).  On return `*result` points at the buffer whose elements hold (index << 16 | .).
+template <typename KeyFn>
+__device__ inline u32* s16_sort(int M, int cap, KeyFn key, u32* smem) {
+    const size_t n = ((size_t)cap + 3) / 4 * 4;
+    u32 *a = smem, *b = smem + n;
+    u16* cnt = reinterpret_cast<u16*>(smem + 2 * n);
+    u32* wsum = smem + 2 * n + (size_t)kS16Bins * kS16Threads / 2;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < M; i += kS16Threads) a[i] = (key(i) & 0xffffu) | ((u32)i << 16);
+    __syncthreads();
+    int pass = 0;
+    for (int s = 0; s < 16; s += 4, ++pass)
+        if (s16_pass(a, b, M, s, cnt, wsum, pass)) { u32* t = a; a = b; b = t; }
+    for (int i = tid; i < M; i += kS16Threads) {
+        const u32 idx = a[i] >> 16;
+        a[i] = (key((int)idx) >> 16) | (idx << 16);
+    }
+    __syncthreads();
+    for (int s = 0; s < 16; s += 4, ++pass)
+        if (s16_pass(a, b, M, s, cnt, wsum, pass)) { u32* t = a; a = b; b = t; }
+    return a;
+}
+
 }  // namespace yb

@@ -56,16 +56,12 @@ __device__ __forceinline__ bool py_cell(double v, int G, int& cell) {
     return true;
 }
 
-__global__ void __launch_bounds__(128) build_targets_kernel(const TargetArgs a) {
-    extern __shared__ GtSlot s_gt[];
-    const int b = blockIdx.x;
-    int n = a.n_gt[b];
-    n = n < 0 ? 0 : (n > a.max_gt ? a.max_gt : n);
+// Phase 1 of both assignment kernels: every ground truth of image b -> its slot key and fp32 row.
+__device__ __forceinline__ bool assign_slots(const TargetArgs& a, int b, int n, GtSlot* s_gt) {
     const double ow = a.letterbox[b * 5 + 0], oh = a.letterbox[b * 5 + 1];
     const double sc = a.letterbox[b * 5 + 2], pt = a.letterbox[b * 5 + 3], pl = a.letterbox[b * 5 + 4];
     const double img = (double)a.img;
     bool bad = false;
-
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double* L = a.labels + ((size_t)b * a.max_gt + i) * 5;
         // :159-162 — python double arithmetic, left to right, no fusion
@@ -104,15 +100,27 @@ __global__ void __launch_bounds__(128) build_targets_kernel(const TargetArgs a) 
         g.x = (float)xc; g.y = (float)yc; g.w = (float)wd; g.h = (float)hd;  // :195-197
         s_gt[i] = g;
     }
+    return bad;
+}
+
+// :193 — the slot is already owned by an earlier ground truth of the same image
+__device__ __forceinline__ bool slot_taken(const GtSlot* s_gt, int i, uint32_t key) {
+    for (int j = 0; j < i; ++j)
+        if (s_gt[j].key == key) return true;
+    return false;
+}
+
+__global__ void __launch_bounds__(128) build_targets_kernel(const TargetArgs a) {
+    extern __shared__ GtSlot s_gt[];
+    const int b = blockIdx.x;
+    int n = a.n_gt[b];
+    n = n < 0 ? 0 : (n > a.max_gt ? a.max_gt : n);
+    const bool bad = assign_slots(a, b, n, s_gt);
     __syncthreads();
     const int row = 5 + a.nc;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const GtSlot g = s_gt[i];
-        if (g.key == 0xffffffffu) continue;
-        bool first = true;
-        for (int j = 0; j < i; ++j)
-            if (s_gt[j].key == g.key) { first = false; break; }  // :193 slot already owned
-        if (!first) continue;
+        if (g.key == 0xffffffffu || slot_taken(s_gt, i, g.key)) continue;
         const int s = g.key >> 28, an = (g.key >> 24) & 15, gy = (g.key >> 12) & 4095, gx = g.key & 4095;
         const int G = a.G[s];
         float* t = a.tgt[s] + ((((size_t)b * G + gy) * G + gx) * a.A + an) * row;
@@ -122,6 +130,53 @@ __global__ void __launch_bounds__(128) build_targets_kernel(const TargetArgs a) 
         else if (a.nc > 1) t[5 + g.cls] = 1.0f;        // :205
     }
     if (bad && a.status) atomicOr(a.status, 1);
+}
+
+// Sparse form of the same assignment: instead of dense (G,G,A,5+nc) tensors the
+// winners are appended to per-scale positive lists (row index + entry id), their target rows are
+// kept as 32-byte entries, and a 1-bit-per-row map marks them for the objectness pass.
+__global__ void __launch_bounds__(128) assign_sparse_kernel(const TargetArgs a, const SparseOut o) {
+    extern __shared__ GtSlot s_gt[];
+    const int b = blockIdx.x;
+    int n = a.n_gt[b];
+    n = n < 0 ? 0 : (n > a.max_gt ? a.max_gt : n);
+    const bool bad = assign_slots(a, b, n, s_gt);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const GtSlot g = s_gt[i];
+        if (g.key == 0xffffffffu || slot_taken(s_gt, i, g.key)) continue;
+        const int s = g.key >> 28, an = (g.key >> 24) & 15, gy = (g.key >> 12) & 4095, gx = g.key & 4095;
+        const int G = a.G[s];
+        const uint32_t r = (uint32_t)((((size_t)b * G + gy) * G + gx) * a.A + an);
+        const uint32_t e = (uint32_t)b * a.max_gt + i;
+        o.entries[e] = SparseEntry{g.x, g.y, g.w, g.h, a.nc == 1 ? 0 : g.cls, 0, 0, 0};  // :201-202
+        atomicOr(o.bits + o.bits_begin[s] + (r >> 5), 1u << (r & 31));
+        const int k = atomicAdd(o.pos_count + s, 1);
+        o.pos_list[o.list_begin[s] + k] = r;
+        o.pos_ent[o.list_begin[s] + k] = e;
+    }
+    if (bad && a.status) atomicOr(a.status, 1);
+}
+
+int launch_assign_sparse(const double* labels, const int* n_gt, const double* letterbox, const float* anchors, int B,
+                         int max_gt, int S, const int* G, int A, int nc, int img_size, int* status,
+                         const SparseOut& o, cudaStream_t st) {
+    TargetArgs a;
+    a.labels = labels; a.n_gt = n_gt; a.letterbox = letterbox; a.anchors = anchors;
+    a.S = S; a.A = A; a.nc = nc; a.max_gt = max_gt; a.img = img_size; a.status = status;
+    for (int s = 0; s < S; ++s) {
+        YB_CHECK_ARG(G[s] > 0 && G[s] <= 4096, "assign: bad grid at scale %d", s);
+        a.G[s] = G[s];
+        a.tgt[s] = nullptr;
+    }
+    if (status) YB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+    if (max_gt == 0 || B == 0) return 0;
+    size_t smem = (size_t)max_gt * sizeof(GtSlot);
+    YB_CHECK_ARG(smem <= 200 * 1024, "assign: max_gt=%d too large", max_gt);
+    if (smem > 48 * 1024)
+        YB_CUDA(cudaFuncSetAttribute(assign_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YB_LAUNCH("assign_sparse_kernel", st, assign_sparse_kernel<<<B, 128, smem, st>>>(a, o));
+    return 0;
 }
 
 }  // namespace yb

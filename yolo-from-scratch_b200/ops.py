@@ -21,6 +21,7 @@ raises.
 import ctypes
 from typing import List, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -202,18 +203,20 @@ def _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=No
         d.w_obj[s] = obj_weights[s]
         d.coef_box[s], d.coef_obj[s], d.coef_cls[s] = coef[s]
         d.pred[s] = preds[s].data_ptr()
-        d.tgt[s] = tgts[s].data_ptr()
+        d.tgt[s] = _ptr(tgts[s])
         d.anchors[s] = ancs[s].data_ptr()
         d.grad[s] = _ptr(grads[s])
     return d
 
 
 def loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want_grad, coef=None, group=None, equal_shards=True,
-                          b_global=None, reduce_fn=None):
+                          b_global=None, reduce_fn=None, sparse=None):
     """Run the fused kernels on device tensors.  Returns (out4, per_scale(S,3), grads list).
 
     `group`: optional torch.distributed process group; the batch is then a shard of a global
     batch and the S*4 partial sums are all-reduced once between the two stages.
+    `sparse`: a `PackedLabels` — targets are assigned on the device from the label lists and handed
+    to the loss in sparse form; `tgts` is then ignored (pass None).
     """
     L = _lib.lib()
     S = len(preds)
@@ -230,14 +233,29 @@ def loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want_grad, coef=No
         import torch.distributed as dist
         world = dist.get_world_size(group)
         b_global = b_global * world if equal_shards else dist_global_batch(preds[0].shape[0], group)
+    if sparse is not None:
+        tgts = [None] * S
     d = _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=b_global)
-    ws_bytes = L.yb_loss_workspace_bytes(ctypes.byref(d))
+    if sparse is None:
+        ws_bytes = L.yb_loss_workspace_bytes(ctypes.byref(d))
+    else:
+        ws_bytes = L.yb_loss_sparse_workspace_bytes(ctypes.byref(d), sparse.max_gt)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     partials = torch.empty(S * 4, dtype=torch.float64, device=dev)
     out4 = torch.empty(4, dtype=torch.float32, device=dev)
     per_scale = torch.empty(S, 3, dtype=torch.float32, device=dev)
     st = _stream()
-    _lib.check(L.yb_loss_partials(ctypes.byref(d), partials.data_ptr(), ws.data_ptr(), ws_bytes, st), "yb_loss_partials")
+    if sparse is None:
+        _lib.check(L.yb_loss_partials(ctypes.byref(d), partials.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                   "yb_loss_partials")
+    else:
+        if sparse.labels.shape[0] != preds[0].shape[0]:
+            raise ValueError("labels and predictions disagree on the batch size")
+        anc_all = torch.stack(list(ancs)).contiguous()  # (S,A,2)
+        _lib.check(L.yb_loss_partials_sparse(ctypes.byref(d), sparse.labels.data_ptr(), sparse.n_gt.data_ptr(),
+                                             sparse.letterbox.data_ptr(), anc_all.data_ptr(), sparse.max_gt,
+                                             int(sparse.img_size), sparse.status.data_ptr(), partials.data_ptr(),
+                                             ws.data_ptr(), ws_bytes, st), "yb_loss_partials_sparse")
     if reduce_fn is not None:
         partials = reduce_fn(partials)          # test hook: emulate the collective on one GPU
     elif world > 1:
@@ -255,10 +273,15 @@ class _YoloLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, nc, obj_weights, group, S, *tensors):
+        sparse = None
+        if isinstance(group, tuple):  # (process group, PackedLabels): targets come from label lists
+            group, sparse = group
         preds, tgts, ancs = tensors[:S], tensors[S:2 * S], tensors[2 * S:3 * S]
         want = [ctx.needs_input_grad[4 + s] for s in range(S)]
-        out4, per_scale, grads = loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want, group=group)
+        out4, per_scale, grads = loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want, group=group,
+                                                       sparse=sparse)
         ctx.set_materialize_grads(False)
+        ctx.sparse = sparse
         ctx.cfg = (nc, obj_weights, group, S, want)
         ctx.fused_grads = grads
         ctx.save_for_backward(*tensors)
@@ -287,12 +310,13 @@ class _YoloLossFn(torch.autograd.Function):
             z = lambda g: 0.0 if g is None else float(g)
             gt_, gb_, go_, gc_ = z(g_total), z(g_bbox), z(g_obj), z(g_cls)
             coef = [(BOX_WEIGHT * gt_ + gb_, obj_weights[s] * gt_ + go_, CLS_WEIGHT * gt_ + gc_) for s in range(S)]
-            _, _, grads = loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want, coef=coef, group=group)
+            _, _, grads = loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want, coef=coef, group=group,
+                                                sparse=ctx.sparse)
         ctx.fused_grads = None
         return none + tuple(grads) + (None,) * (2 * S)
 
 
-def _loss_common(predictions, targets, anchors_list, num_classes, obj_weights, group=None):
+def _loss_common(predictions, targets, anchors_list, num_classes, obj_weights, group=None, sparse=None):
     S = len(predictions)
     if not 1 <= S <= MAX_SCALES:
         raise ValueError(f"1..{MAX_SCALES} scales supported, got {S}")
@@ -302,17 +326,73 @@ def _loss_common(predictions, targets, anchors_list, num_classes, obj_weights, g
         preds, tgts, ancs = [], [], []
         for s in range(S):
             _check_head(predictions[s], f"predictions[{s}]")
-            if predictions[s].shape != targets[s].shape:
+            if sparse is None and predictions[s].shape != targets[s].shape:
                 raise ValueError(f"scale {s}: predictions {tuple(predictions[s].shape)} vs targets {tuple(targets[s].shape)}")
             if predictions[s].shape[4] != 5 + num_classes:
                 raise ValueError(f"scale {s}: last dim {predictions[s].shape[4]} != 5+num_classes")
             preds.append(_f32c(predictions[s], dev))
-            tgts.append(_f32c(targets[s].detach(), dev))
+            # sparse targets: a placeholder keeps the autograd signature (preds, targets, anchors) x S
+            tgts.append(_f32c(targets[s].detach(), dev) if sparse is None else preds[-1].detach())
             ancs.append(_anchors_dev(anchors_list[s], dev))
-        outs = _YoloLossFn.apply(int(num_classes), tuple(float(w) for w in obj_weights), group, S, *preds, *tgts, *ancs)
+        outs = _YoloLossFn.apply(int(num_classes), tuple(float(w) for w in obj_weights),
+                                 group if sparse is None else (group, sparse), S, *preds, *tgts, *ancs)
     if orig_dev != dev:
         outs = tuple(o.to(orig_dev) for o in outs)
     return outs
+
+
+class PackedLabels:
+    """Label lists of a batch on the device, the input of the sparse-target loss:
+    labels (B,max_gt,5) fp64 [class, xc, yc, w, h], n_gt (B) int32, letterbox (B,5) fp64
+    [orig_w, orig_h, scale, pad_top, pad_left] (train.py:136-137), the dataset's img_size."""
+
+    def __init__(self, labels, n_gt, letterbox, img_size):
+        self.labels, self.n_gt, self.letterbox, self.img_size = labels, n_gt, letterbox, int(img_size)
+        self.max_gt = int(labels.shape[1])
+        self.status = torch.zeros(1, dtype=torch.int32, device=labels.device)
+
+    def check(self):
+        """Raise like the reference (IndexError, train.py:193-205) if a label mapped outside the grid."""
+        if int(self.status.item()) != 0:
+            raise IndexError("a label maps outside the grid or the class range (train.py:193-205)")
+
+
+def pack_labels_host(labels: Sequence, img_size: int, letterbox: Optional[Sequence] = None, pin: bool = False):
+    """Host-side packing of per-image label arrays [(n_i,5)] into (labels (B,max_gt,5) f64, n_gt (B) i32,
+    letterbox (B,5) f64) — 40 bytes per ground truth instead of three dense target tensors."""
+    B = len(labels)
+    rows = [torch.as_tensor(l, dtype=torch.float64).reshape(-1, 5) for l in labels]
+    max_gt = max([r.shape[0] for r in rows], default=0)
+    lab = torch.zeros(B, max(max_gt, 1), 5, dtype=torch.float64)
+    n_gt = torch.zeros(B, dtype=torch.int32)
+    for i, r in enumerate(rows):
+        lab[i, :r.shape[0]] = r
+        n_gt[i] = r.shape[0]
+    if letterbox is None:
+        lb = torch.tensor([[img_size, img_size, 1.0, 0.0, 0.0]] * B, dtype=torch.float64).reshape(B, 5)
+    else:
+        lb = torch.as_tensor(np.asarray(letterbox, dtype=np.float64)).reshape(B, 5)
+    if pin:
+        lab, n_gt, lb = lab.pin_memory(), n_gt.pin_memory(), lb.pin_memory()
+    return lab, n_gt, lb
+
+
+def pack_labels(labels: Sequence, img_size: int, letterbox: Optional[Sequence] = None) -> PackedLabels:
+    dev = _device()
+    lab, n_gt, lb = pack_labels_host(labels, img_size, letterbox)
+    return PackedLabels(lab.to(dev), n_gt.to(dev), lb.to(dev), img_size)
+
+
+def yolo_loss_multiscale_labels(predictions, labels, anchors_list, num_classes=1, img_size=640, letterbox=None,
+                                group=None):
+    """yolo_loss_multiscale (train.py:840-886) fed by LABEL LISTS instead of dense targets: the
+    assignment of YOLODataset.__getitem__ (:147-205) runs on the device and reaches the loss in
+    sparse form.  `labels`: per-image (n_i,5) arrays, or a PackedLabels already on the device.
+    Returns the same (total, sum bbox, sum obj, sum cls) as the dense call on the reference's targets."""
+    S = min(len(predictions), len(anchors_list), len(MULTISCALE_OBJ_WEIGHTS))
+    packed = labels if isinstance(labels, PackedLabels) else pack_labels(labels, img_size, letterbox)
+    return _loss_common(list(predictions[:S]), [None] * S, list(anchors_list[:S]), num_classes,
+                        MULTISCALE_OBJ_WEIGHTS[:S], group=group, sparse=packed)
 
 
 def yolo_loss(predictions, targets, anchors, num_classes=1):
