@@ -31,6 +31,14 @@ extern "C" {
 #define YB_MAX_SCALES 4
 #define YB_MAX_ANCHORS 8
 
+/* Layout of head tensors (pred / grad): the model-output contract of train.py:608-609,
+ * (B, H, W, A, 5+nc), or — f-2, SURVEY 8f — the head conv's own output (B, A*(5+nc), H, W), i.e. the
+ * tensor BEFORE the reference's view/permute/contiguous: the path then reads the conv output directly
+ * and that full read+write pass (and its backward) disappears.  Dense targets always keep the
+ * reference layout; row indices, candidate order and all results are identical in both layouts. */
+#define YB_LAYOUT_BHWAC 0
+#define YB_LAYOUT_NCHW 1
+
 #define YB_EINVAL (-1)   /* bad argument (shape, null pointer, alignment) */
 #define YB_EWORKSPACE (-2) /* workspace too small */
 
@@ -101,6 +109,7 @@ typedef struct yb_loss_desc {
     const float* tgt[YB_MAX_SCALES];
     const float* anchors[YB_MAX_SCALES];
     float* grad[YB_MAX_SCALES];     /* nullable: forward only (torch.no_grad callers) */
+    int layout;                     /* YB_LAYOUT_* of pred and grad */
 } yb_loss_desc;
 
 size_t yb_loss_workspace_bytes(const yb_loss_desc* d);
@@ -171,6 +180,7 @@ typedef struct yb_heads_desc {
     float img_size;
     const float* pred[YB_MAX_SCALES];
     const float* anchors[YB_MAX_SCALES];
+    int layout;                     /* YB_LAYOUT_* of pred (filter: both; decode/eval: BHWAC only) */
 } yb_heads_desc;
 
 size_t yb_filter_workspace_bytes(const yb_heads_desc* d);

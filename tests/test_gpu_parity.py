@@ -324,6 +324,103 @@ def test_sparse_label_loss_packed_letterbox_and_errors(yb):
         pk.check()
 
 
+# ---- NCHW head layout -----------------------------------------------------------------
+@pytest.mark.parametrize("B,nc,grids,img", [(4, 1, (80, 40, 20), 640), (2, 80, (20, 10, 5), 160), (3, 3, (13, 7, 5), 104)])
+def test_nchw_heads_give_identical_results(yb, B, nc, grids, img):
+    """The *_nchw entry points read the head convs' own output (B, A*(5+nc), H, W): loss values equal
+    the reference-layout call, gradients equal its gradients permuted back, candidates / keep sets are
+    identical, for dense targets and for label lists.  (13,7,5) exercises H*W not divisible by 4."""
+    g = torch.Generator().manual_seed(31 + nc)
+    raw = [torch.randn(B, 3 * (5 + nc), G, G, generator=g).cuda() for G in grids]
+    heads = [yb.heads_from_nchw(r) for r in raw]
+    labels = _random_labels(np.random.default_rng(nc + 2), B, nc, 30)
+    tg = yb.build_targets(labels, ANCH, list(grids), nc, img)
+    to_nchw = lambda t: t.permute(0, 3, 4, 1, 2).reshape(t.shape[0], -1, t.shape[1], t.shape[2])
+    rp = [h.clone().requires_grad_(True) for h in heads]
+    ref = yb.yolo_loss_multiscale(rp, tg, ANCH, nc)
+    ref[0].backward()
+    for targets in (tg, labels):
+        xp = [r.clone().requires_grad_(True) for r in raw]
+        out = yb.yolo_loss_multiscale_nchw(xp, targets, ANCH, nc, img)
+        out[0].backward()
+        for a, b in zip(out, ref):
+            close(a, b, rtol=1e-6, atol=1e-7)
+        for x, r in zip(xp, rp):
+            close(x.grad, to_nchw(r.grad), rtol=1e-6, atol=1e-10)
+    for conf in (0.5, 0.001):
+        d0 = yb.detect_batch(heads, ANCH, img, nc, conf, 0.4)
+        d1 = yb.detect_batch_nchw(raw, ANCH, img, nc, conf, 0.4)
+        assert torch.equal(d0["counts"], d1["counts"]) and torch.equal(d0["n_keep"], d1["n_keep"])
+        for b in range(B):
+            m, k = int(d0["counts"][b]), int(d0["n_keep"][b])
+            assert torch.equal(d0["boxes"][b, :m], d1["boxes"][b, :m])
+            assert torch.equal(d0["scores"][b, :m], d1["scores"][b, :m])
+            assert torch.equal(d0["classes"][b, :m], d1["classes"][b, :m])
+            assert torch.equal(d0["keep"][b, :k], d1["keep"][b, :k])
+
+
+# ---- eval_epoch counting (SURVEY 8f-1) -------------------------------------------------------------
+@pytest.mark.parametrize("name", ["e640", "e320"])
+def test_eval_epoch_matches_reference_golden(yb, golden, name):
+    """yb.eval_epoch on the preset heads/targets the UNMODIFIED reference's eval_epoch was run on
+    (oracle/make_golden.py): precision/recall/F1 exact (they are ratios of integer counts), loss 1e-5."""
+    g = golden("eval")
+    img, nc, B, nb, conf, iou = g[f"{name}_cfg"]
+    nc, nb = int(nc), int(nb)
+
+    class Model:
+        anchors = ANCH
+        k = 0
+
+        def eval(self):
+            return self
+
+        def __call__(self, imgs):
+            heads = [torch.from_numpy(g[f"{name}_b{self.k}_head{s}"]) for s in range(3)]
+            self.k += 1
+            return heads
+    loader = []
+    for k in range(nb):
+        tg = [torch.from_numpy(g[f"{name}_b{k}_tgt{s}"]) for s in range(3)]
+        loader.append((torch.zeros(int(B), 3, 8, 8), [[tg[s][b] for s in range(3)] for b in range(int(B))]))
+    res = yb.eval_epoch(Model(), loader, torch.device("cpu"), num_classes=nc, iou_threshold=float(iou),
+                        conf_threshold=float(conf))
+    want = g[f"{name}_result"]
+    close(res[0], want[0])
+    assert tuple(res[1:]) == tuple(want[1:])
+
+
+@pytest.mark.parametrize("nc,B,grids,conf,iou", [(1, 4, (80, 40, 20), 0.5, 0.5), (80, 2, (20, 10, 5), 0.25, 0.3),
+                                                  (3, 3, (13, 7, 5), 0.5, 0.0)])
+def test_eval_counts_vs_oracle(yb, nc, B, grids, conf, iou):
+    """Counts are integers: exact against the oracle, on heads steered towards their targets so that
+    all three counters and both sides of the IoU threshold are populated."""
+    g = torch.Generator().manual_seed(5 + nc)
+    rng = np.random.default_rng(nc)
+    img = grids[0] * 8
+    labels = _random_labels(rng, B, nc, 40)
+    tg = [t.cpu() for t in yb.build_targets(labels, ANCH, list(grids), nc, img)]
+    heads = [torch.randn(t.shape, generator=g) for t in tg]
+    for s, t in enumerate(tg):  # copy decoded-target-ish logits into half of the positive rows
+        pos = (t[..., 4] > 0.5).nonzero()
+        for b, gy, gx, a in pos.tolist()[::2]:
+            G = t.shape[1]
+            xc, yc, w, h = [float(v) for v in t[b, gy, gx, a, 0:4]]
+            sx = min(max((xc * G - gx + 0.5) / 2, 0.02), 0.98)
+            sy = min(max((yc * G - gy + 0.5) / 2, 0.02), 0.98)
+            sw = min(max(np.sqrt(w * rng.uniform(0.6, 1.6) * 640.0 / float(ANCH[s][a, 0])) / 2, 0.02), 0.98)
+            sh = min(max(np.sqrt(h * rng.uniform(0.6, 1.6) * 640.0 / float(ANCH[s][a, 1])) / 2, 0.02), 0.98)
+            lg = lambda p: float(np.log(p / (1 - p)))
+            heads[s][b, gy, gx, a, 0:4] = torch.tensor([lg(sx), lg(sy), lg(sw), lg(sh)])
+            heads[s][b, gy, gx, a, 4] = 2.0
+    want = R.eval_counts(heads, tg, ANCH, conf, iou)
+    got = yb.eval_counts([h.cuda() for h in heads], [t.cuda() for t in tg], ANCH, conf, iou)
+    assert tuple(int(v) for v in got.cpu()) == tuple(want)
+    assert min(want) > 0 or iou == 0.0
+    again = yb.eval_counts(heads, tg, ANCH, conf, iou, out=got)          # CPU tensors staged; accumulates
+    assert tuple(int(v) for v in again.cpu()) == tuple(2 * w for w in want)
+
+
 # ---- target assignment ------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["a", "b", "c", "d", "e", "f", "g"])
 def test_build_targets_golden_bitexact(yb, golden, name):

@@ -225,3 +225,23 @@ def test_live_reference_agrees(reference_module):
     a = ref.yolo_loss(x, tg, ANCH[2], 3)
     b = R.single_scale_loss(x, tg, ANCH[2], 3)
     assert [float(v) for v in a] == [float(v) for v in b]
+
+
+@pytest.mark.parametrize("name", ["e640", "e320"])
+def test_eval_counts_match_reference_eval_epoch(golden, name):
+    """Oracle restatement of eval_epoch's counting (train.py:993-1024) against the four values the
+    unmodified reference returned on the same preset heads/targets (oracle/make_golden.py)."""
+    g = golden("eval")
+    img, nc, B, nb, conf, iou = g[f"{name}_cfg"]
+    tp = fp = fn = 0
+    loss = 0.0
+    for k in range(int(nb)):
+        heads = [torch.from_numpy(g[f"{name}_b{k}_head{s}"]) for s in range(3)]
+        tg = [torch.from_numpy(g[f"{name}_b{k}_tgt{s}"]) for s in range(3)]
+        a, b, c = R.eval_counts(heads, tg, R.default_anchors(), float(conf), float(iou))
+        tp, fp, fn = tp + a, fp + b, fn + c
+        loss += float(R.multiscale_loss(heads, tg, R.default_anchors(), int(nc))[0])
+    want = g[f"{name}_result"]
+    assert loss / int(nb) == want[0]
+    assert R.eval_metrics(tp, fp, fn) == tuple(want[1:])
+    assert tp > 0 and fp > 0 and fn > 0

@@ -12,6 +12,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_in
 MAX_SCALES = 4
 MAX_ANCHORS = 8
 NMS_GRAPH, NMS_BITMASK = 0, 1
+LAYOUT_BHWAC, LAYOUT_NCHW = 0, 1
 LIB_NAME = "libyolo_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
@@ -26,6 +27,7 @@ class LossDesc(Structure):
         ("coef_obj", c_float * MAX_SCALES), ("coef_cls", c_float * MAX_SCALES),
         ("pred", c_void_p * MAX_SCALES), ("tgt", c_void_p * MAX_SCALES),
         ("anchors", c_void_p * MAX_SCALES), ("grad", c_void_p * MAX_SCALES),
+        ("layout", c_int),
     ]
 
 
@@ -35,6 +37,7 @@ class HeadsDesc(Structure):
         ("S", c_int), ("B", c_int), ("A", c_int), ("nc", c_int),
         ("H", c_int * MAX_SCALES), ("W", c_int * MAX_SCALES), ("img_size", c_float),
         ("pred", c_void_p * MAX_SCALES), ("anchors", c_void_p * MAX_SCALES),
+        ("layout", c_int),
     ]
 
 

@@ -118,6 +118,7 @@ extern "C" int yb_eval_counts(const yb_heads_desc* d, const float* const* target
     YB_CHECK_ARG(d && targets_host && counts3, "eval_counts: null argument");
     YB_CHECK_ARG(d->S >= 1 && d->S <= YB_MAX_SCALES && d->B >= 0 && d->A > 0 && d->A <= YB_MAX_ANCHORS && d->nc >= 0,
                  "eval_counts: bad S/B/A/nc");
+    YB_CHECK_ARG(d->layout == YB_LAYOUT_BHWAC, "eval_counts: only the reference layout (B,H,W,A,5+nc) is supported");
     if (d->B == 0) return 0;
     EvalArgs a;
     a.S = d->S; a.A = d->A; a.row = 5 + d->nc;

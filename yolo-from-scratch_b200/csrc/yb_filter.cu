@@ -26,6 +26,7 @@ struct FilterScale {
     const float* pred;
     const float* anchors;
     uint32_t rows;         // rows per image at this scale = H*W*A
+    uint32_t hw;           // H*W
     uint32_t tile_begin;   // first tile (within an image) of this scale
     uint32_t group_begin;  // first group (within an image) of this scale
     float inv_w, inv_h;
@@ -33,7 +34,7 @@ struct FilterScale {
 };
 
 struct FilterArgs {
-    int S, A, nc, cap, G;
+    int S, A, nc, cap, G, nchw;
     uint32_t row, tiles_per_img, groups_per_img;
     float img, inv_img, conf;
     int stage_ok;              // shared-memory staging available for this row length
@@ -46,6 +47,21 @@ struct FilterArgs {
     int64_t* classes;
     int* counts;
 };
+
+// float offset of channel 0 of row r (within image b, scale L) and the distance between its channels;
+// NCHW (f-2): the head conv's own output (B, A*row, H, W)
+__device__ __forceinline__ size_t frow_base(const FilterArgs& a, const FilterScale& L, uint32_t b, uint32_t r,
+                                            uint32_t& cstride) {
+    if (!a.nchw) {
+        cstride = 1u;
+        return ((size_t)b * L.rows + r) * a.row;
+    }
+    uint32_t cell, an;
+    L.d_A.divmod(r, cell, an);
+    const uint32_t HW = L.hw;
+    cstride = HW;
+    return ((size_t)(b * (uint32_t)a.A + an) * a.row) * HW + cell;
+}
 
 __device__ __forceinline__ int group_scale(const FilterArgs& a, uint32_t group) {
     int s = 0;
@@ -60,12 +76,16 @@ __global__ void __launch_bounds__(kFTile) filter_count_kernel(const FilterArgs a
     const FilterScale& L = a.sc[group_scale(a, group)];
     const uint32_t tile0 = (group - L.group_begin) * a.G;        // tile within the scale
     const uint32_t ntiles = (L.rows + kFTile - 1) / kFTile;
-    const float* col = L.pred + (size_t)b * L.rows * a.row + 4;  // objectness column
     float x[kFMaxGroup];
 #pragma unroll
     for (int k = 0; k < kFMaxGroup; ++k) {
         const uint32_t r = (tile0 + k) * kFTile + threadIdx.x;
-        x[k] = (k < a.G && r < L.rows) ? __ldg(col + (size_t)r * a.row) : -INFINITY;
+        x[k] = -INFINITY;
+        if (k < a.G && r < L.rows) {
+            uint32_t cs;
+            const size_t base = frow_base(a, L, b, r, cs);
+            x[k] = __ldg(L.pred + base + 4 * (size_t)cs);  // objectness
+        }
     }
 #pragma unroll
     for (int k = 0; k < kFMaxGroup; ++k) {
@@ -188,7 +208,7 @@ __global__ void __launch_bounds__(kFTile) filter_emit_kernel(const FilterArgs a)
     const float* g = L.pred + base;
 
     // dense groups: stage through shared memory
-    const bool staged = a.stage_ok && total * 4 >= (int)nrows;
+    const bool staged = a.stage_ok && !a.nchw && total * 4 >= (int)nrows;
     if (staged) {
         const uint32_t nfl = nrows * a.row;
         if ((base & 3) == 0 && (nfl & 3) == 0) {
@@ -207,7 +227,9 @@ __global__ void __launch_bounds__(kFTile) filter_emit_kernel(const FilterArgs a)
         bool pass = false;
         float so = 0.0f;
         if (rl < nrows) {
-            const float xo = staged ? s_tile[rl * a.row + 4] : __ldg(g + (size_t)rl * a.row + 4);
+            uint32_t cs;
+            const size_t rb = frow_base(a, L, b, row0 + rl, cs);
+            const float xo = staged ? s_tile[rl * a.row + 4] : __ldg(L.pred + rb + 4 * (size_t)cs);
             so = sigmoidf_ref(xo);
             pass = so > a.conf;
         }
@@ -245,9 +267,11 @@ __global__ void __launch_bounds__(kFTile) filter_emit_kernel(const FilterArgs a)
             x0 = x[0]; x1r = x[1]; x2r = x[2]; x3r = x[3];
             class_max(a.nc, [&](int c) { return x[5 + c]; }, cprob, cid);
         } else {
-            const float* x = g + (size_t)rl * a.row;
-            x0 = __ldg(x); x1r = __ldg(x + 1); x2r = __ldg(x + 2); x3r = __ldg(x + 3);
-            class_max(a.nc, [&](int c) { return __ldg(x + 5 + c); }, cprob, cid);
+            uint32_t cs;
+            const float* x = L.pred + frow_base(a, L, b, r, cs);
+            const size_t st = cs;
+            x0 = __ldg(x); x1r = __ldg(x + st); x2r = __ldg(x + 2 * st); x3r = __ldg(x + 3 * st);
+            class_max(a.nc, [&](int c) { return __ldg(x + (size_t)(5 + c) * st); }, cprob, cid);
         }
         // decode (:1154) with the model's img_size
         const float bx = decode_xy(x0, (float)gx, L.inv_w);
@@ -273,6 +297,8 @@ static int filter_fill(const yb_heads_desc* d, FilterArgs& a) {
     YB_CHECK_ARG(d->S >= 1 && d->S <= YB_MAX_SCALES && d->B >= 0 && d->A > 0 && d->A <= YB_MAX_ANCHORS && d->nc >= 1,
                  "filter: bad S/B/A/nc (nc must be >= 1, train.py:1184-1189)");
     a.S = d->S; a.A = d->A; a.nc = d->nc; a.row = 5 + d->nc;
+    YB_CHECK_ARG(d->layout == YB_LAYOUT_BHWAC || d->layout == YB_LAYOUT_NCHW, "filter: unknown layout %d", d->layout);
+    a.nchw = d->layout == YB_LAYOUT_NCHW ? 1 : 0;
     a.img = d->img_size; a.inv_img = 1.0f / d->img_size;
     // tiles per CTA: about 44 KB of head rows, at most kFMaxGroup
     {
@@ -288,6 +314,7 @@ static int filter_fill(const yb_heads_desc* d, FilterArgs& a) {
         FilterScale& L = a.sc[s];
         L.pred = d->pred[s]; L.anchors = d->anchors[s];
         L.rows = (uint32_t)d->H[s] * d->W[s] * d->A;
+        L.hw = (uint32_t)d->H[s] * d->W[s];
         L.tile_begin = tile;
         L.group_begin = group;
         const uint32_t nt = (L.rows + kFTile - 1) / kFTile;

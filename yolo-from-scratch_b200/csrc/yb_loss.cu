@@ -162,10 +162,14 @@ struct LossScale {
     float inv_w, inv_h;
     float obj_scale;      // coef_obj / (B_global*H*W*A)
     FastDiv d_A, d_W, d_H;
+    // NCHW layout (f-2): pred/grad are (B, A*row, H, W); element (r, c) of canonical row r=(b,gy,gx,a)
+    // lives at ((b*A + a)*row + c)*HW + gy*W + gx
+    uint32_t HW, n_float;
+    FastDiv d_HW;
 };
 
 struct LossArgs {
-    int S, A, nc;
+    int S, A, nc, nchw;
     uint32_t row;        // 5+nc
     uint32_t n_tiles;
     float inv_img, eps;
@@ -177,6 +181,19 @@ struct LossArgs {
     const SparseEntry* entries;  // sparse targets: target rows
     double* partials;    // S*4: {sum(1-ciou), n_pos, sum bce_obj, sum bce_cls}
 };
+
+// offset of channel 0 of canonical row r, and the distance between its channels
+__device__ __forceinline__ size_t row_base(const LossArgs& a, const LossScale& L, uint32_t r, uint32_t& cstride) {
+    if (!a.nchw) {
+        cstride = 1u;
+        return (size_t)r * a.row;
+    }
+    uint32_t cellb, an, b, cell;
+    L.d_A.divmod(r, cellb, an);
+    L.d_HW.divmod(cellb, b, cell);
+    cstride = L.HW;
+    return ((size_t)(b * a.A + an) * a.row) * L.HW + cell;
+}
 
 struct LossWs {
     int pos_count[YB_MAX_SCALES];
@@ -270,6 +287,83 @@ __global__ void __launch_bounds__(kTileRows) loss_main_kernel(const LossArgs a) 
     }
 }
 
+// NCHW variant of the main pass (f-2): walks the gradient tensor (B, A*row, H, W) as a flat float4
+// stream.  84 of 85 channel planes (nc=80) are pure zero stores; an objectness plane is a coalesced
+// read of the logits (4 bytes per row instead of one 128-byte DRAM line per row in the reference
+// layout), the targets' objectness (dense: reference layout; sparse: the bit map) and a coalesced
+// store of the gradient.
+template <bool SPARSE>
+__global__ void __launch_bounds__(kTileRows) loss_main_nchw_kernel(const LossArgs a) {
+    __shared__ float s_warp[kTileRows / 32];
+    double cta_sum[YB_MAX_SCALES];
+#pragma unroll
+    for (int s = 0; s < YB_MAX_SCALES; ++s) cta_sum[s] = 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int s = 0;
+#pragma unroll
+        for (int k = 1; k < YB_MAX_SCALES; ++k)
+            if (k < a.S && tile >= a.sc[k].tile_begin) s = k;
+        const LossScale& L = a.sc[s];
+        const uint32_t e0 = ((tile - L.tile_begin) * kTileRows + threadIdx.x) * 4u;  // first float of this thread
+        float bce = 0.0f;
+        if (e0 < L.n_float) {
+            uint32_t plane, within;
+            L.d_HW.divmod(e0, plane, within);
+            float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t e = e0 + k;
+                if (e < L.n_float) {
+                    uint32_t ba, c;
+                    a.d_row.divmod(plane, ba, c);
+                    if (c == 4u) {
+                        uint32_t b, an;
+                        L.d_A.divmod(ba, b, an);
+                        const uint32_t r = (b * L.HW + within) * (uint32_t)a.A + an;  // canonical row
+                        const float x = __ldg(L.pred + e);
+                        float t;
+                        if (SPARSE) t = ((__ldg(L.bits + (r >> 5)) >> (r & 31)) & 1u) ? 1.0f : 0.0f;
+                        else t = __ldg(L.tgt + (size_t)r * a.row + 4);
+                        bce += bce_logits_ref(x, t);
+                        o[k] = (sigmoidf_ref(x) - t) * L.obj_scale;
+                        if (!SPARSE && t > 0.5f) {
+                            const int slot = atomicAdd(a.pos_count + s, 1);
+                            a.pos_list[L.list_begin + slot] = r;
+                        }
+                    }
+                }
+                if (++within == L.HW) { within = 0; ++plane; }
+            }
+            if (L.grad) {
+                if (e0 + 4u <= L.n_float) {
+                    *reinterpret_cast<float4*>(L.grad + e0) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+                    for (uint32_t k = 0; e0 + k < L.n_float; ++k) L.grad[e0 + k] = o[k];
+                }
+            }
+        }
+        const float wsum = warp_sum(bce);
+        if (lane == 0) s_warp[warp] = wsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tsum = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kTileRows / 32; ++k) tsum += s_warp[k];
+#pragma unroll
+            for (int k = 0; k < YB_MAX_SCALES; ++k)
+                if (k == s) cta_sum[k] += (double)tsum;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < YB_MAX_SCALES; ++s)
+            if (s < a.S && cta_sum[s] != 0.0) atomicAdd(a.partials + s * 4 + 2, cta_sum[s]);
+    }
+}
+
 // one warp per positive row
 template <bool SPARSE>
 __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
@@ -283,8 +377,10 @@ __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
         double acc_box = 0.0, acc_cls = 0.0;
         for (uint32_t k = gwarp; k < P; k += nwarps) {
             const uint32_t r = a.pos_list[L.list_begin + k];
-            const float* x = L.pred + (size_t)r * a.row;
-            const float* t = SPARSE ? nullptr : L.tgt + (size_t)r * a.row;
+            uint32_t cs;
+            const size_t xb = row_base(a, L, r, cs);
+            const float* x = L.pred + xb;
+            const float* t = SPARSE ? nullptr : L.tgt + (size_t)r * a.row;  // dense targets keep the reference layout
             SparseEntry ent = {0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0};
             if (SPARSE) ent = a.entries[a.pos_ent[L.list_begin + k]];
             uint32_t cell, an, gy_b, gx, gy, bi;
@@ -292,7 +388,7 @@ __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
             L.d_W.divmod(cell, gy_b, gx);
             L.d_H.divmod(gy_b, bi, gy);
             const float aw = __ldg(L.anchors + an * 2), ah = __ldg(L.anchors + an * 2 + 1);
-            const float xr[4] = {x[0], x[1], x[2], x[3]};
+            const float xr[4] = {x[0], x[(size_t)cs], x[2 * (size_t)cs], x[3 * (size_t)cs]};
             const float p[4] = {decode_xy(xr[0], (float)gx, L.inv_w), decode_xy(xr[1], (float)gy, L.inv_h),
                                 decode_wh(xr[2], aw, a.inv_img), decode_wh(xr[3], ah, a.inv_img)};
             const float tb[4] = {SPARSE ? ent.x : t[0], SPARSE ? ent.y : t[1], SPARSE ? ent.w : t[2],
@@ -302,10 +398,10 @@ __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
             // class BCE, lanes stride over classes
             float cls = 0.0f;
             for (int c = lane; c < a.nc; c += 32) {
-                const float xc = x[5 + c];
+                const float xc = x[(size_t)(5 + c) * cs];
                 const float tc = SPARSE ? (c == ent.cls ? 1.0f : 0.0f) : t[5 + c];
                 cls += bce_logits_ref(xc, tc);
-                if (L.grad) L.grad[(size_t)r * a.row + 5 + c] = sigmoidf_ref(xc) - tc;
+                if (L.grad) L.grad[xb + (size_t)(5 + c) * cs] = sigmoidf_ref(xc) - tc;
             }
             cls = warp_sum(cls);
             if (L.grad && lane < 4) {
@@ -320,7 +416,7 @@ __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
                     const float u = 2.0f * sgm;
                     g = (((gp[lane] * (anc * a.inv_img)) * (2.0f * u)) * 2.0f) * ds;
                 }
-                L.grad[(size_t)r * a.row + lane] = g;
+                L.grad[xb + (size_t)lane * cs] = g;
             }
             acc_box += (double)l;
             acc_cls += (double)cls;
@@ -359,9 +455,10 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const FinalizeArgs f
         const float k_box = (float)((double)f.coef_box[s] / Pg);
         const float k_cls = a.nc > 0 ? (float)((double)f.coef_cls[s] / (Pg * (double)a.nc)) : 0.0f;
         for (uint32_t k = gwarp; k < P; k += nwarps) {
-            float* g = L.grad + (size_t)a.pos_list[L.list_begin + k] * a.row;
-            if (lane < 4) g[lane] *= k_box;
-            for (int c = lane; c < a.nc; c += 32) g[5 + c] *= k_cls;
+            uint32_t cs;
+            float* g = L.grad + row_base(a, L, a.pos_list[L.list_begin + k], cs);
+            if (lane < 4) g[(size_t)lane * cs] *= k_box;
+            for (int c = lane; c < a.nc; c += 32) g[(size_t)(5 + c) * cs] *= k_cls;
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -405,6 +502,7 @@ static int loss_validate(const yb_loss_desc* d, bool need_ptrs, bool sparse = fa
     YB_CHECK_ARG(d->S >= 1 && d->S <= YB_MAX_SCALES, "loss: S=%d out of range", d->S);
     YB_CHECK_ARG(d->B >= 0 && d->A > 0 && d->A <= YB_MAX_ANCHORS && d->nc >= 0, "loss: bad B/A/nc");
     YB_CHECK_ARG(d->B_global >= d->B, "loss: B_global < B");
+    YB_CHECK_ARG(d->layout == YB_LAYOUT_BHWAC || d->layout == YB_LAYOUT_NCHW, "loss: unknown layout %d", d->layout);
     unsigned long long tot = 0;
     for (int s = 0; s < d->S; ++s) {
         YB_CHECK_ARG(d->H[s] > 0 && d->W[s] > 0, "loss: bad grid at scale %d", s);
@@ -423,6 +521,7 @@ static int loss_validate(const yb_loss_desc* d, bool need_ptrs, bool sparse = fa
 
 static void loss_fill_args(const yb_loss_desc* d, void* ws, LossArgs& a) {
     a.S = d->S; a.A = d->A; a.nc = d->nc; a.row = 5 + d->nc;
+    a.nchw = d->layout == YB_LAYOUT_NCHW ? 1 : 0;
     a.inv_img = 1.0f / d->img_size; a.eps = d->eps;
     a.d_row = FastDiv(a.row);
     LossWs* w = reinterpret_cast<LossWs*>(ws);
@@ -435,7 +534,11 @@ static void loss_fill_args(const yb_loss_desc* d, void* ws, LossArgs& a) {
         L.bits = nullptr;
         L.rows = (uint32_t)((unsigned long long)d->B * d->H[s] * d->W[s] * d->A);
         L.tile_begin = tile; L.list_begin = list;
-        tile += (L.rows + kTileRows - 1) / kTileRows;
+        L.HW = (uint32_t)d->H[s] * (uint32_t)d->W[s];
+        L.n_float = L.rows * a.row;
+        L.d_HW = FastDiv(L.HW);
+        // reference layout: one tile = kTileRows rows; NCHW: one tile = kTileRows float4 of the flat tensor
+        tile += a.nchw ? (L.n_float + kTileRows * 4 - 1) / (kTileRows * 4) : (L.rows + kTileRows - 1) / kTileRows;
         list += L.rows;
         L.H = d->H[s]; L.W = d->W[s];
         L.inv_w = 1.0f / (float)d->W[s]; L.inv_h = 1.0f / (float)d->H[s];
@@ -522,7 +625,8 @@ extern "C" int yb_loss_partials(const yb_loss_desc* d, double* partials, void* w
     if (a.n_tiles == 0) return 0;
     const int sms = sm_count();
     int blocks = (int)(a.n_tiles < (uint32_t)(sms * 8) ? a.n_tiles : (uint32_t)(sms * 8));
-    YB_LAUNCH("loss_main_kernel", st, loss_main_kernel<false><<<blocks, kTileRows, 0, st>>>(a));
+    if (a.nchw) YB_LAUNCH("loss_main_nchw_kernel", st, loss_main_nchw_kernel<false><<<blocks, kTileRows, 0, st>>>(a));
+    else YB_LAUNCH("loss_main_kernel", st, loss_main_kernel<false><<<blocks, kTileRows, 0, st>>>(a));
     YB_LAUNCH("loss_positive_kernel", st, loss_positive_kernel<false><<<sms * 2, 256, 0, st>>>(a));
     return 0;
 }
@@ -577,7 +681,8 @@ extern "C" int yb_loss_partials_sparse(const yb_loss_desc* d, const double* labe
     if (rc) return rc;
     const int sms = sm_count();
     int blocks = (int)(a.n_tiles < (uint32_t)(sms * 8) ? a.n_tiles : (uint32_t)(sms * 8));
-    YB_LAUNCH("loss_main_kernel", st, loss_main_kernel<true><<<blocks, kTileRows, 0, st>>>(a));
+    if (a.nchw) YB_LAUNCH("loss_main_nchw_kernel", st, loss_main_nchw_kernel<true><<<blocks, kTileRows, 0, st>>>(a));
+    else YB_LAUNCH("loss_main_kernel", st, loss_main_kernel<true><<<blocks, kTileRows, 0, st>>>(a));
     YB_LAUNCH("loss_positive_kernel", st, loss_positive_kernel<true><<<sms * 2, 256, 0, st>>>(a));
     return 0;
 }

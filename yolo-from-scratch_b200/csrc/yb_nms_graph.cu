@@ -280,12 +280,16 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
 struct RowAux { u32 rank; u32 cls; };
 
 // Per-warp shared memory of the edge kernel.
+struct RowRec {  // 32 bytes: one address computation serves the box, its area and (rarely) rank/class
+    float4 box;
+    float area;
+    u32 rank, cls, pad;
+};
 struct EdgeWarp {
-    float4 row[kTile];      // rows of tile I
+    RowRec row[kTile];      // rows of tile I
     float4 col[kTile];      // columns of the current chunk: 4 surviving sub-tiles x 8 boxes
-    float rarea[kTile];
     float carea[kTile];
-    RowAux raux[kTile];
+    RowAux caux[kTile];     // score rank and class of the chunk's columns
     u32 tl[kTile];          // compaction scratch: surviving tiles of the current step
     u32 sub[kTile * kSubs + 8];  // queue of surviving sub-tile ids (J*kSubs+s); < 4 left over between steps
     unsigned char item[kTile * kSubs];  // (sub-tile slot << 5) | row, packed work list of a chunk
@@ -320,10 +324,12 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
     const int cp = slot_ok ? (int)(my_sub * kSub) + (lane & (kSub - 1)) : 0;
     const bool cvalid = slot_ok && cp < M;
     float4 cq = make_float4(far, far, far, far);
-    if (cvalid) cq = sb[cp];
+    RowAux cx = {0xffffffffu, 0u};
+    if (cvalid) { cq = sb[cp]; cx.rank = srank[cp]; cx.cls = scls[cp]; }
     const float cw = cq.z - cq.x, ch = cq.w - cq.y;
     w.col[lane] = cq;
     w.carea[lane] = cw * ch;
+    w.caux[lane] = cx;
 
     // row culling against the statistics of each slot; pack the surviving (row, slot) items
     int n_items = 0;
@@ -354,8 +360,9 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
         const u32 item = w.item[act ? idx : it];
         const int i = item & 31u, slot = item >> 5;
         const int c = slot * kSub + (lane & (kSub - 1));
-        const float4 r = w.row[i];
-        const float rarea = w.rarea[i];
+        const RowRec* rr = &w.row[i];
+        const float4 r = rr->box;
+        const float rarea = rr->area;
         const float4 q = w.col[c];
         const float qarea = w.carea[c];
         const float left = fmaxf(r.x, q.x), right = fminf(r.z, q.z);
@@ -370,11 +377,11 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
         const bool amb = act && (all_exact || !(fabsf(d) > __fmaf_rn(tt, kEps, kTiny)));
         if (!__any_sync(0xffffffffu, pr || amb)) continue;
         // rare: a candidate edge.  Exact arithmetic where needed, validity, same class, each pair once.
-        const RowAux ra = w.raux[i];
+        const RowAux ra = {rr->rank, rr->cls};
         const int qp = (int)(sub[slot] * kSub) + (lane & (kSub - 1));
         const bool qvalid = act && qp < M;
-        u32 crank = 0xffffffffu, ccls = 0u;
-        if (qvalid) { crank = srank[qp]; ccls = scls[qp]; }
+        const RowAux ca = w.caux[c];
+        const u32 crank = ca.rank, ccls = ca.cls;
         if (amb) {
             // torchvision devIoU with a = the higher-scored box
             const bool row_a = ra.rank < crank;
@@ -400,7 +407,7 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kEdgeThreads, 3) graph_edge_kernel(const GArgs a) {
+__global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs a) {
     __shared__ EdgeWarp s_w[kEdgeThreads / 32];
     const int lane = threadIdx.x & 31;
     EdgeWarp& w = s_w[threadIdx.x >> 5];
@@ -438,9 +445,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 3) graph_edge_kernel(const GArgs
         const float rS = rw * rh;
         const float rw_t = t2 * rw, rh_t = t2 * rh, rS_t = t2 * rS;
         __syncwarp();
-        w.row[lane] = rq;
-        w.rarea[lane] = rS;
-        w.raux[lane] = RowAux{rrank, rcls};
+        w.row[lane] = RowRec{rq, rS, rrank, rcls, 0u};
         __syncwarp();
         const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
         const u32 icmin = __float_as_uint(ia.z), icmax = __float_as_uint(ia.w);
@@ -667,7 +672,7 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     }
     const dim3 ggrid((a.tcap + kGatherThreads / 32 - 1) / (kGatherThreads / 32), B);
     YB_LAUNCH("graph_gather_kernel", st, graph_gather_kernel<<<ggrid, kGatherThreads, 0, st>>>(a));
-    const int ctas = sm_count() * 4;
+    const int ctas = sm_count() * 4;  // 4 resident CTAs per SM (launch bounds)
     YB_LAUNCH("graph_edge_kernel", st, graph_edge_kernel<<<ctas, kEdgeThreads, 0, st>>>(a));
     const size_t dyn = (size_t)((cap + 31) / 32) * 4 * 4;
     YB_CHECK_ARG(dyn <= 200 * 1024, "nms(graph): cap too large for the resolve kernel");

@@ -2,7 +2,8 @@
 
 The reference (`train.py`) has no plugin API; its callers resolve `decode_predictions`,
 `ciou_loss`, `yolo_loss`, `yolo_loss_multiscale` through module globals at call time
-(train.py:796, :818, :874, :909, :987, :993, :1154), `predict` imports
+(train.py:796, :818, :874, :909, :987, :993, :1154), the CLI resolves `eval_epoch` the same way
+(:1413, :1436, :1523), `predict` imports
 `torchvision.ops.batched_nms` at call time (:1232), and target assignment lives in
 `YOLODataset.__getitem__` / `compute_anchor_iou` (:108-131, :147-205).  `install(train_module)`
 rebinds exactly those names; the file on disk is untouched.
@@ -51,14 +52,18 @@ def _make_getitem(train_module):
     return __getitem__
 
 
-def install(train_module, patch_torchvision=True, patch_dataset=True):
-    """Rebind the hot-path names of an imported reference `train` module.  Idempotent."""
+def install(train_module, patch_torchvision=True, patch_dataset=True, patch_eval=True):
+    """Rebind the hot-path names of an imported reference `train` module.  Idempotent.
+    patch_eval also swaps `eval_epoch` (its per-anchor python loop becomes one kernel)."""
     if getattr(train_module, _MARK, False):
         return train_module
     saved = {}
     for name in PATCHED_FUNCTIONS:
         saved[name] = getattr(train_module, name)
         setattr(train_module, name, getattr(ops, name))
+    if patch_eval and hasattr(train_module, "eval_epoch"):
+        saved["eval_epoch"] = train_module.eval_epoch
+        train_module.eval_epoch = ops.eval_epoch
     if patch_dataset and hasattr(train_module, "YOLODataset"):
         cls = train_module.YOLODataset
         saved["YOLODataset.__getitem__"] = cls.__getitem__
@@ -82,6 +87,8 @@ def uninstall(train_module):
         return
     for name in PATCHED_FUNCTIONS:
         setattr(train_module, name, saved[name])
+    if "eval_epoch" in saved:
+        train_module.eval_epoch = saved["eval_epoch"]
     if "YOLODataset.__getitem__" in saved:
         train_module.YOLODataset.__getitem__ = saved["YOLODataset.__getitem__"]
         train_module.YOLODataset.compute_anchor_iou = saved["YOLODataset.compute_anchor_iou"]

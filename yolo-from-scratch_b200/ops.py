@@ -187,19 +187,36 @@ def ciou_loss(pred_boxes: torch.Tensor, target_boxes: torch.Tensor, eps=CIOU_EPS
 # --------------------------------------------------------------------------------------------
 # a-3 / a-4 fused loss
 # --------------------------------------------------------------------------------------------
-def _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=None, img_size=LOSS_DECODE_IMG_SIZE):
+LAYOUT_BHWAC, LAYOUT_NCHW = _lib.LAYOUT_BHWAC, _lib.LAYOUT_NCHW
+
+
+def _grid(p: torch.Tensor, layout: int):
+    """(H, W) of a head tensor: (B,H,W,A,5+nc) or, NCHW, (B, A*(5+nc), H, W)."""
+    return (p.shape[2], p.shape[3]) if layout == LAYOUT_NCHW else (p.shape[1], p.shape[2])
+
+
+def heads_from_nchw(raw: torch.Tensor, num_anchors: int = 3) -> torch.Tensor:
+    """The reference's own head reshape (train.py:608-609): (B, A*(5+nc), H, W) -> contiguous
+    (B, H, W, A, 5+nc).  The *_nchw entry points make this pass unnecessary; tests use it."""
+    B, C, H, W = raw.shape
+    return raw.view(B, num_anchors, C // num_anchors, H, W).permute(0, 3, 4, 1, 2).contiguous()
+
+
+def _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=None, img_size=LOSS_DECODE_IMG_SIZE,
+                    layout=LAYOUT_BHWAC):
     S = len(preds)
     d = LossDesc()
     d.S = S
+    d.layout = layout
     d.B = preds[0].shape[0]
     d.B_global = d.B if B_global is None else int(B_global)
-    d.A = preds[0].shape[3]
+    d.A = ancs[0].shape[0]
     d.nc = nc
     d.img_size = img_size
     d.eps = CIOU_EPS
     d.w_box, d.w_cls = BOX_WEIGHT, CLS_WEIGHT
     for s in range(S):
-        d.H[s], d.W[s] = preds[s].shape[1], preds[s].shape[2]
+        d.H[s], d.W[s] = _grid(preds[s], layout)
         d.w_obj[s] = obj_weights[s]
         d.coef_box[s], d.coef_obj[s], d.coef_cls[s] = coef[s]
         d.pred[s] = preds[s].data_ptr()
@@ -210,7 +227,7 @@ def _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=No
 
 
 def loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want_grad, coef=None, group=None, equal_shards=True,
-                          b_global=None, reduce_fn=None, sparse=None):
+                          b_global=None, reduce_fn=None, sparse=None, layout=LAYOUT_BHWAC):
     """Run the fused kernels on device tensors.  Returns (out4, per_scale(S,3), grads list).
 
     `group`: optional torch.distributed process group; the batch is then a shard of a global
@@ -235,7 +252,7 @@ def loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want_grad, coef=No
         b_global = b_global * world if equal_shards else dist_global_batch(preds[0].shape[0], group)
     if sparse is not None:
         tgts = [None] * S
-    d = _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=b_global)
+    d = _fill_loss_desc(preds, tgts, ancs, grads, nc, obj_weights, coef, B_global=b_global, layout=layout)
     if sparse is None:
         ws_bytes = L.yb_loss_workspace_bytes(ctypes.byref(d))
     else:
@@ -273,15 +290,15 @@ class _YoloLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, nc, obj_weights, group, S, *tensors):
-        sparse = None
-        if isinstance(group, tuple):  # (process group, PackedLabels): targets come from label lists
-            group, sparse = group
+        sparse, layout = None, LAYOUT_BHWAC
+        if isinstance(group, tuple):  # (process group, PackedLabels or None, layout)
+            group, sparse, layout = group
         preds, tgts, ancs = tensors[:S], tensors[S:2 * S], tensors[2 * S:3 * S]
         want = [ctx.needs_input_grad[4 + s] for s in range(S)]
         out4, per_scale, grads = loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want, group=group,
-                                                       sparse=sparse)
+                                                       sparse=sparse, layout=layout)
         ctx.set_materialize_grads(False)
-        ctx.sparse = sparse
+        ctx.sparse, ctx.layout = sparse, layout
         ctx.cfg = (nc, obj_weights, group, S, want)
         ctx.fused_grads = grads
         ctx.save_for_backward(*tensors)
@@ -311,12 +328,13 @@ class _YoloLossFn(torch.autograd.Function):
             gt_, gb_, go_, gc_ = z(g_total), z(g_bbox), z(g_obj), z(g_cls)
             coef = [(BOX_WEIGHT * gt_ + gb_, obj_weights[s] * gt_ + go_, CLS_WEIGHT * gt_ + gc_) for s in range(S)]
             _, _, grads = loss_forward_backward(preds, tgts, ancs, nc, obj_weights, want, coef=coef, group=group,
-                                                sparse=ctx.sparse)
+                                                sparse=ctx.sparse, layout=ctx.layout)
         ctx.fused_grads = None
         return none + tuple(grads) + (None,) * (2 * S)
 
 
-def _loss_common(predictions, targets, anchors_list, num_classes, obj_weights, group=None, sparse=None):
+def _loss_common(predictions, targets, anchors_list, num_classes, obj_weights, group=None, sparse=None,
+                 layout=LAYOUT_BHWAC):
     S = len(predictions)
     if not 1 <= S <= MAX_SCALES:
         raise ValueError(f"1..{MAX_SCALES} scales supported, got {S}")
@@ -325,17 +343,25 @@ def _loss_common(predictions, targets, anchors_list, num_classes, obj_weights, g
     with torch.cuda.device(dev):
         preds, tgts, ancs = [], [], []
         for s in range(S):
-            _check_head(predictions[s], f"predictions[{s}]")
-            if sparse is None and predictions[s].shape != targets[s].shape:
-                raise ValueError(f"scale {s}: predictions {tuple(predictions[s].shape)} vs targets {tuple(targets[s].shape)}")
-            if predictions[s].shape[4] != 5 + num_classes:
-                raise ValueError(f"scale {s}: last dim {predictions[s].shape[4]} != 5+num_classes")
+            if layout == LAYOUT_NCHW:
+                p, A = predictions[s], len(anchors_list[s])
+                if p.dim() != 4 or p.shape[1] != A * (5 + num_classes):
+                    raise ValueError(f"scale {s}: NCHW head must be (B, {A}*(5+num_classes), H, W), got {tuple(p.shape)}")
+                if sparse is None and tuple(targets[s].shape) != (p.shape[0], p.shape[2], p.shape[3], A, 5 + num_classes):
+                    raise ValueError(f"scale {s}: targets {tuple(targets[s].shape)} do not match the head")
+            else:
+                _check_head(predictions[s], f"predictions[{s}]")
+                if sparse is None and predictions[s].shape != targets[s].shape:
+                    raise ValueError(f"scale {s}: predictions {tuple(predictions[s].shape)} vs targets {tuple(targets[s].shape)}")
+                if predictions[s].shape[4] != 5 + num_classes:
+                    raise ValueError(f"scale {s}: last dim {predictions[s].shape[4]} != 5+num_classes")
             preds.append(_f32c(predictions[s], dev))
             # sparse targets: a placeholder keeps the autograd signature (preds, targets, anchors) x S
             tgts.append(_f32c(targets[s].detach(), dev) if sparse is None else preds[-1].detach())
             ancs.append(_anchors_dev(anchors_list[s], dev))
-        outs = _YoloLossFn.apply(int(num_classes), tuple(float(w) for w in obj_weights),
-                                 group if sparse is None else (group, sparse), S, *preds, *tgts, *ancs)
+        packed_cfg = group if (sparse is None and layout == LAYOUT_BHWAC) else (group, sparse, layout)
+        outs = _YoloLossFn.apply(int(num_classes), tuple(float(w) for w in obj_weights), packed_cfg, S,
+                                 *preds, *tgts, *ancs)
     if orig_dev != dev:
         outs = tuple(o.to(orig_dev) for o in outs)
     return outs
@@ -357,12 +383,17 @@ class PackedLabels:
             raise IndexError("a label maps outside the grid or the class range (train.py:193-205)")
 
 
-def pack_labels_host(labels: Sequence, img_size: int, letterbox: Optional[Sequence] = None, pin: bool = False):
+def pack_labels_host(labels: Sequence, img_size: int, letterbox: Optional[Sequence] = None, pin: bool = False,
+                     max_gt: Optional[int] = None):
     """Host-side packing of per-image label arrays [(n_i,5)] into (labels (B,max_gt,5) f64, n_gt (B) i32,
     letterbox (B,5) f64) — 40 bytes per ground truth instead of three dense target tensors."""
     B = len(labels)
     rows = [torch.as_tensor(l, dtype=torch.float64).reshape(-1, 5) for l in labels]
-    max_gt = max([r.shape[0] for r in rows], default=0)
+    need = max([r.shape[0] for r in rows], default=0)
+    if max_gt is None:
+        max_gt = need
+    elif max_gt < need:
+        raise ValueError(f"max_gt={max_gt} < {need} labels in one image")
     lab = torch.zeros(B, max(max_gt, 1), 5, dtype=torch.float64)
     n_gt = torch.zeros(B, dtype=torch.int32)
     for i, r in enumerate(rows):
@@ -395,6 +426,24 @@ def yolo_loss_multiscale_labels(predictions, labels, anchors_list, num_classes=1
                         MULTISCALE_OBJ_WEIGHTS[:S], group=group, sparse=packed)
 
 
+def yolo_loss_multiscale_nchw(raw_heads, targets, anchors_list, num_classes=1, img_size=640, letterbox=None,
+                              group=None):
+    """yolo_loss_multiscale on the head convs' OWN outputs (B, A*(5+nc), H, W) — SURVEY 8f-2: the
+    view/permute/contiguous of train.py:608-609 (a full read+write of every head, plus its backward)
+    is not needed; the gradient comes back in the same NCHW layout, ready for the conv backward.
+    `targets`: the reference's dense targets [(B,G,G,A,5+nc)], or label lists / PackedLabels (then
+    the assignment runs on the device, as in yolo_loss_multiscale_labels)."""
+    S = min(len(raw_heads), len(anchors_list), len(MULTISCALE_OBJ_WEIGHTS))
+    dense = len(targets) > 0 and isinstance(targets[0], torch.Tensor) and targets[0].dim() == 5
+    if isinstance(targets, PackedLabels) or not dense:
+        packed = targets if isinstance(targets, PackedLabels) else pack_labels(targets, img_size, letterbox)
+        return _loss_common(list(raw_heads[:S]), [None] * S, list(anchors_list[:S]), num_classes,
+                            MULTISCALE_OBJ_WEIGHTS[:S], group=group, sparse=packed, layout=LAYOUT_NCHW)
+    S = min(S, len(targets))
+    return _loss_common(list(raw_heads[:S]), list(targets[:S]), list(anchors_list[:S]), num_classes,
+                        MULTISCALE_OBJ_WEIGHTS[:S], group=group, layout=LAYOUT_NCHW)
+
+
 def yolo_loss(predictions, targets, anchors, num_classes=1):
     """train.py:781-838.  Returns (total, bbox, obj, cls) for one scale."""
     return _loss_common([predictions], [targets], [anchors], num_classes, (1.0,))
@@ -405,6 +454,62 @@ def yolo_loss_multiscale(predictions, targets, anchors_list, num_classes=1):
     S = min(len(predictions), len(targets), len(anchors_list), len(MULTISCALE_OBJ_WEIGHTS))  # zip() semantics (:873)
     return _loss_common(list(predictions[:S]), list(targets[:S]), list(anchors_list[:S]), num_classes,
                         MULTISCALE_OBJ_WEIGHTS[:S])
+
+
+# --------------------------------------------------------------------------------------------
+# f-1 eval_epoch's detection counting
+# --------------------------------------------------------------------------------------------
+EVAL_DECODE_IMG_SIZE = 640.0  # train.py:993 — eval_epoch decodes with the default img_size
+
+
+def eval_counts(predictions, targets, anchors_list, conf_threshold=0.5, iou_threshold=0.5, out=None):
+    """The TP/FP/FN loop of eval_epoch (train.py:993-1024) for one batch, all scales, in one kernel.
+    Returns an int64 device tensor [TP, FP, FN]; pass `out` to accumulate over batches (no sync)."""
+    dev = _device()
+    S = min(len(predictions), len(targets), len(anchors_list))
+    with torch.cuda.device(dev):
+        preds = [_f32c(p.detach(), dev) for p in predictions[:S]]
+        tgts = [_f32c(t.detach(), dev) for t in targets[:S]]
+        for s in range(S):
+            _check_head(preds[s], f"predictions[{s}]")
+            if preds[s].shape != tgts[s].shape:
+                raise ValueError(f"scale {s}: predictions {tuple(preds[s].shape)} vs targets {tuple(tgts[s].shape)}")
+        ancs = [_anchors_dev(a, dev) for a in anchors_list[:S]]
+        d = _heads_desc(preds, ancs, EVAL_DECODE_IMG_SIZE, preds[0].shape[4] - 5)
+        if out is None:
+            out = torch.zeros(3, dtype=torch.int64, device=dev)
+        tptr = (ctypes.c_void_p * MAX_SCALES)(*[t.data_ptr() for t in tgts])
+        _lib.check(_lib.lib().yb_eval_counts(ctypes.byref(d), tptr, float(conf_threshold), float(iou_threshold),
+                                             out.data_ptr(), _stream()), "yb_eval_counts")
+    return out
+
+
+def eval_epoch(model, loader, device, num_classes=1, iou_threshold=0.5, conf_threshold=0.5):
+    """Drop-in for train.eval_epoch (train.py:960-1032): same arguments, same four return values
+    (avg_loss, precision %, recall %, F1 %).  The loss and the detection counting run on the GPU
+    path; the counters stay on the device until the end of the epoch (one synchronisation instead of
+    2 x rows `.item()` calls per batch)."""
+    model.eval()
+    anchors_list = model.anchors
+    counts = None
+    loss_sum = None
+    n_batches = 0
+    with torch.no_grad():
+        for imgs, targets in loader:
+            imgs = imgs.to(device)
+            S = len(targets[0])
+            targets_batch = [torch.stack([t[s] for t in targets]).to(device) for s in range(S)]  # :973-977
+            preds = model(imgs)
+            loss = yolo_loss_multiscale(preds, targets_batch, anchors_list, num_classes)[0]        # :987
+            loss_sum = loss.detach().double().cuda() if loss_sum is None else loss_sum + loss.detach().double().cuda()
+            counts = eval_counts(preds, targets_batch, anchors_list, conf_threshold, iou_threshold, out=counts)
+            n_batches += 1
+    tp, fp, fn = (0, 0, 0) if counts is None else [int(v) for v in counts.cpu().tolist()]
+    precision = tp / (tp + fp) if (tp + fp) > 0 else 0                                            # :1026-1029
+    recall = tp / (tp + fn) if (tp + fn) > 0 else 0
+    f1 = 2 * precision * recall / (precision + recall) if (precision + recall) > 0 else 0
+    avg_loss = (float(loss_sum) if loss_sum is not None else 0.0) / n_batches                      # :1031 (ZeroDivisionError on an empty loader, like the reference)
+    return avg_loss, precision * 100, recall * 100, f1 * 100
 
 
 # --------------------------------------------------------------------------------------------
@@ -470,18 +575,20 @@ def build_targets(labels: Sequence, anchors_list, grid_sizes: Sequence[int], num
 # --------------------------------------------------------------------------------------------
 # a-6 candidate filter, a-7 NMS
 # --------------------------------------------------------------------------------------------
-def _heads_desc(preds, ancs, img_size, nc):
+def _heads_desc(preds, ancs, img_size, nc, layout=LAYOUT_BHWAC):
     d = HeadsDesc()
-    d.S, d.B, d.A, d.nc = len(preds), preds[0].shape[0], preds[0].shape[3], nc
+    d.S, d.B, d.A, d.nc = len(preds), preds[0].shape[0], ancs[0].shape[0], nc
     d.img_size = float(img_size)
+    d.layout = layout
     for s, p in enumerate(preds):
-        d.H[s], d.W[s] = p.shape[1], p.shape[2]
+        d.H[s], d.W[s] = _grid(p, layout)
         d.pred[s] = p.data_ptr()
         d.anchors[s] = ancs[s].data_ptr()
     return d
 
 
-def filter_candidates(predictions, anchors_list, img_size, num_classes=1, conf_threshold=0.5, letterbox=None):
+def filter_candidates(predictions, anchors_list, img_size, num_classes=1, conf_threshold=0.5, letterbox=None,
+                      layout=LAYOUT_BHWAC):
     """Per-scale body of predict() (train.py:1152-1229) for a batch: decode, sigmoid, objectness
     filter, class max, pixel xyxy with letterbox reverse, score; P3->P4->P5 order preserved.
 
@@ -493,12 +600,16 @@ def filter_candidates(predictions, anchors_list, img_size, num_classes=1, conf_t
     S = len(predictions)
     with torch.cuda.device(dev):
         preds = [_f32c(p.detach(), dev) for p in predictions]
-        for s, p in enumerate(preds):
-            _check_head(p, f"predictions[{s}]")
         ancs = [_anchors_dev(a, dev) for a in anchors_list[:S]]
+        for s, p in enumerate(preds):
+            if layout == LAYOUT_NCHW:
+                if p.dim() != 4 or p.shape[1] != ancs[s].shape[0] * (5 + int(num_classes)):
+                    raise ValueError(f"predictions[{s}]: NCHW head must be (B, A*(5+nc), H, W), got {tuple(p.shape)}")
+            else:
+                _check_head(p, f"predictions[{s}]")
         B = preds[0].shape[0]
-        cap = sum(p.shape[1] * p.shape[2] * p.shape[3] for p in preds)
-        d = _heads_desc(preds, ancs, img_size, int(num_classes))
+        cap = sum(_grid(p, layout)[0] * _grid(p, layout)[1] * ancs[s].shape[0] for s, p in enumerate(preds))
+        d = _heads_desc(preds, ancs, img_size, int(num_classes), layout)
         L = _lib.lib()
         ws_bytes = L.yb_filter_workspace_bytes(ctypes.byref(d))
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
@@ -611,7 +722,7 @@ def nms(boxes, scores, iou_threshold, algo=NMS_GRAPH):
 
 
 def detect_batch(predictions, anchors_list, img_size, num_classes=1, conf_threshold=0.5, iou_threshold=0.4,
-                 letterbox=None, trick_max_numel=TRICK_MAX_NUMEL_CUDA, algo=NMS_GRAPH):
+                 letterbox=None, trick_max_numel=TRICK_MAX_NUMEL_CUDA, algo=NMS_GRAPH, layout=LAYOUT_BHWAC):
     """predict() lines 1152-1238 for a whole batch on the GPU: decode + filter + global NMS.
 
     Returns a dict of device tensors: boxes (B,cap,4), scores, classes, counts (candidates per
@@ -619,12 +730,20 @@ def detect_batch(predictions, anchors_list, img_size, num_classes=1, conf_thresh
     Nothing is synchronised; use `detections_to_lists` for the reference's list-of-tuples form.
     """
     boxes, scores, classes, counts = filter_candidates(predictions, anchors_list, img_size, num_classes,
-                                                       conf_threshold, letterbox)
+                                                       conf_threshold, letterbox, layout)
     with torch.cuda.device(boxes.device):
         keep, n_keep, ws = batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel, algo,
                                               return_workspace=True)
     return {"boxes": boxes, "scores": scores, "classes": classes, "counts": counts, "keep": keep, "n_keep": n_keep,
             "iou_threshold": float(iou_threshold), "trick_max_numel": int(trick_max_numel), "algo": algo, "nms_ws": ws}
+
+
+def detect_batch_nchw(raw_heads, anchors_list, img_size, num_classes=1, conf_threshold=0.5, iou_threshold=0.4,
+                      letterbox=None, trick_max_numel=TRICK_MAX_NUMEL_CUDA, algo=NMS_GRAPH):
+    """detect_batch on the head convs' own outputs (B, A*(5+nc), H, W); same candidates,
+    same order, same keep sets as detect_batch on the permuted heads."""
+    return detect_batch(raw_heads, anchors_list, img_size, num_classes, conf_threshold, iou_threshold, letterbox,
+                        trick_max_numel, algo, layout=LAYOUT_NCHW)
 
 
 def pack_detections(det):
