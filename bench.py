@@ -51,6 +51,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--layout", default="bhwac", choices=["bhwac", "nchw"],
+                    help="head layout of the device-resident step: the reference's (B,H,W,A,5+nc) or the head conv's own "
+                         "NCHW output (SURVEY 8f-2)")
+    ap.add_argument("--targets", default="dense", choices=["dense", "labels"],
+                    help="dense reference targets, or label lists assigned on the device (SURVEY 8f-4)")
     ap.add_argument("--no-torch-gpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -204,6 +209,7 @@ def reference_main(args, rank):
 
 def workload_config(args, world, n_sets=4):
     return {
+        "head_layout": args.layout, "targets": args.targets,
         "workload": f"BASELINE {'configs[1]' if (args.nc, args.img, args.batch) == (1, 640, 64) else 'variant'}: nc={args.nc} heads at {args.img}x{args.img}, {args.batch} images/GPU, "
                     f"<= {MAX_GT} GT boxes/image, randn heads, conf {args.conf}, iou {args.iou}",
         "global_batch": args.batch * world, "images_per_gpu": args.batch, "img_size": args.img, "nc": args.nc,
@@ -232,9 +238,9 @@ def b200_main(args, rank, local_rank, world):
         # the other single-GPU BASELINE configs, device-resident only, short runs (parity is in tests/)
         import copy
         others = {}
-        for name, (nc, img, batch, conf) in OTHER_CONFIGS.items():
+        for name, (nc, img, batch, conf, layout, targets) in OTHER_CONFIGS.items():
             a2 = copy.copy(args)
-            a2.nc, a2.img, a2.batch, a2.conf = nc, img, batch, conf
+            a2.nc, a2.img, a2.batch, a2.conf, a2.layout, a2.targets = nc, img, batch, conf, layout, targets
             a2.steps, a2.warmup = max(3, min(args.steps, 6)), 3
             try:
                 o = run_workload(a2, rank, local_rank, world, dev, group, lib, full=False)
@@ -249,9 +255,12 @@ def b200_main(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
 
 
-OTHER_CONFIGS = {  # BASELINE.json configs[2], configs[3]: (nc, img, images/GPU, conf)
-    "configs[2] nc80 640^2 B64 conf0.001": (80, 640, 64, 0.001),
-    "configs[3] nc80 1280^2 B32 conf0.001": (80, 1280, 32, 0.001),
+OTHER_CONFIGS = {  # BASELINE.json configs[2], configs[3]: (nc, img, images/GPU, conf, head layout, targets)
+    "configs[2] nc80 640^2 B64 conf0.001": (80, 640, 64, 0.001, "bhwac", "dense"),
+    "configs[3] nc80 1280^2 B32 conf0.001": (80, 1280, 32, 0.001, "bhwac", "dense"),
+    # the same work on the 'next' rows of SURVEY 8f: NCHW conv output read directly + label-list targets
+    "configs[1] nc1 640^2 B64 conf0.5, NCHW heads + label lists": (1, 640, 64, 0.5, "nchw", "labels"),
+    "configs[2] nc80 640^2 B64 conf0.001, NCHW heads + label lists": (80, 640, 64, 0.001, "nchw", "labels"),
 }
 
 
@@ -268,6 +277,8 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     weights = ops.MULTISCALE_OBJ_WEIGHTS
 
     # n_sets input sets per rank, on the device and (full run) mirrored in pinned host memory
+    layout = ops.LAYOUT_NCHW if args.layout == "nchw" else ops.LAYOUT_BHWAC
+    use_labels = args.targets == "labels"
     dev_sets, host_sets, label_sets = [], [], []
     for k in range(n_sets):
         seed = 1234 + 1000 * k + 100000 * rank
@@ -275,7 +286,12 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         labels = make_labels(np.random.default_rng(4321 + k + 1000 * rank), B, nc)
         tg = ops.build_targets(labels, anchors, grids, nc, img)
         d_heads = [h.to(dev) for h in heads]
-        dev_sets.append((d_heads, tg))
+        if layout == ops.LAYOUT_NCHW:  # the same values as the head conv would have produced them
+            d_heads = [h.permute(0, 3, 4, 1, 2).reshape(h.shape[0], -1, h.shape[1], h.shape[2]).contiguous()
+                       for h in d_heads]
+        packed = ops.pack_labels_host(labels, img, max_gt=MAX_GT)
+        packed = ops.PackedLabels(packed[0].to(dev), packed[1].to(dev), packed[2].to(dev), img)
+        dev_sets.append((d_heads, tg, packed))
         if full:
             host_sets.append(([h.pin_memory() for h in heads], [t.cpu().pin_memory() for t in tg]))
             label_sets.append(ops.pack_labels_host(labels, img, pin=True, max_gt=MAX_GT))
@@ -303,13 +319,15 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
     def step(i, conf=None, record=None):
-        heads, tg = dev_sets[i % n_sets]
+        heads, tg, packed = dev_sets[i % n_sets]
         if record:
             record[0].record()
-        out4, per_scale, grads = ops.loss_forward_backward(heads, tg, anchors, nc, weights, [True] * 3, group=group)
+        out4, per_scale, grads = ops.loss_forward_backward(heads, None if use_labels else tg, anchors, nc, weights,
+                                                           [True] * 3, group=group, sparse=packed if use_labels else None,
+                                                           layout=layout)
         if record:
             record[1].record()
-        det = ops.detect_batch(heads, anchors, img, nc, args.conf if conf is None else conf, args.iou)
+        det = ops.detect_batch(heads, anchors, img, nc, args.conf if conf is None else conf, args.iou, layout=layout)
         if record:
             record[2].record()
         return out4, det
@@ -371,12 +389,15 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         k["share"] = k["ms_per_step"] / ksum if ksum else 0.0
 
     # ---- e2e through the public API with host buffers ---------------------------------------------
-    e2e = e2e_labels = None
+    e2e = e2e_labels = e2e_graph = None
     if full:
         e2e = run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier,
                       max_over_ranks)
         e2e_labels = run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier,
                              max_over_ranks, label_sets=label_sets)
+        if world == 1:
+            e2e_graph = run_e2e_graph(args, yb, ops, dev, world, host_sets, label_sets, anchors, grids, n_sets, barrier,
+                                      max_over_ranks)
 
     # ---- variants: other confidence thresholds (device-resident, detect only) ---------------------
     variants = {}
@@ -389,8 +410,8 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
             n_it = max(5, args.steps // 3)
             a.record()
             for i in range(n_it):
-                heads, _ = dev_sets[i % n_sets]
-                det = ops.detect_batch(heads, anchors, img, nc, conf, args.iou)
+                heads = dev_sets[i % n_sets][0]
+                det = ops.detect_batch(heads, anchors, img, nc, conf, args.iou, layout=layout)
             b.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / n_it
@@ -418,16 +439,18 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     sm_mhz = clocks.get("sm_mhz") or 1965.0
 
     # ---- HBM-bound kernels: algorithmic bytes / measured launch time --------------------
-    pos = float(np.mean([sum(float((t[..., 4] > 0.5).sum()) for t in tg) for _, tg in dev_sets]))
+    pos = float(np.mean([sum(float((t[..., 4] > 0.5).sum()) for t in ds[1]) for ds in dev_sets]))
     M_tot = float(np.mean(cand_counts))
     sector = min(row_bytes, 32)
     alg_bytes = {
         # T (dense grad write) + obj sectors of pred and target + positive rows of pred and target
-        "loss_main_kernel": T_bytes + 2 * rows * sector + 2 * pos * row_bytes,
+        "loss_main_kernel": T_bytes + (1 if use_labels else 2) * rows * sector + 2 * pos * row_bytes,
+        # NCHW: the objectness logits are contiguous planes (4 B per row); dense targets keep their sectors
+        "loss_main_nchw_kernel": T_bytes + rows * 4 + (rows / 8 if use_labels else rows * sector),
         # objectness sector of every row
-        "filter_count_kernel": rows * sector,
+        "filter_count_kernel": rows * (4 if args.layout == "nchw" else sector),
         # objectness sector of every row again + the candidate rows + 28 B of output per candidate
-        "filter_emit_kernel": rows * sector + M_tot * row_bytes + 28 * M_tot,
+        "filter_emit_kernel": rows * (4 if args.layout == "nchw" else sector) + M_tot * row_bytes + 28 * M_tot,
     }
     hbm_kernels = {}
     for name, a_bytes in alg_bytes.items():
@@ -486,7 +509,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         "config": workload_config(args, world, n_sets),
         "loss_fwd_bwd_ms": loss_ms, "decode_nms_ms": det_ms, "decode_nms_images_per_s": B * world / (det_ms * 1e-3),
         "candidates_per_image": float(np.mean(cand_counts)) / B, "kept_per_image": float(np.mean(keep_counts)) / B,
-        "e2e": e2e, "e2e_labels": e2e_labels, "gpu_launches": int(launches), "kernels": kernels,
+        "e2e": e2e, "e2e_labels": e2e_labels, "e2e_graph": e2e_graph, "gpu_launches": int(launches), "kernels": kernels,
         "roofline": roofline, "hbm_kernels": hbm_kernels, "roofline_nms": nms_roof, "cpu_baseline": cpu_baseline,
         "torch_gpu_baseline": torch_gpu, "clocks": clocks, "variants": variants,
     }
@@ -605,6 +628,88 @@ def run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(np.mean(d2h_acc)),
             "api": api + ".backward() + detect_batch + pack_detections; pinned host tensors, H2D / compute / D2H "
                    "pipelined over 3 input slots, timed by host wall clock around all steps"}
+
+
+def run_e2e_graph(args, yb, ops, dev, world, host_sets, label_sets, anchors, grids, n_sets, barrier, max_over_ranks):
+    """e2e with the step captured as a CUDA graph (yb.HotPathGraph, label-list targets): per step the
+    pinned host heads + packed labels are copied into a graph's static inputs, the graph is replayed,
+    and the 4 losses + detection rows are copied back.  Three graphs = three pipeline slots."""
+    B, img, nc = args.batch, args.img, args.nc
+    comp = torch.cuda.current_stream()
+    h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    n_slots = 3
+    slots = []
+    for k in range(n_slots):
+        hp = yb.HotPathGraph(B, img, nc, anchors, args.conf, args.iou, max_gt=MAX_GT, targets="labels")
+        slots.append({"hp": hp, "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
+                      "loss_host": torch.empty(4, dtype=torch.float32).pin_memory(),
+                      "off_host": torch.empty(B + 1, dtype=torch.int32).pin_memory(),
+                      "off_ready": torch.cuda.Event(), "rows_done": torch.cuda.Event(),
+                      "det_host": torch.empty(B * sum(G * G * 3 for G in grids), 6, dtype=torch.float32).pin_memory()})
+    h2d = tensor_bytes(host_sets[0][0]) + tensor_bytes(list(label_sets[0]))
+    d2h_acc = []
+
+    def enqueue_h2d(i):
+        sl = slots[i % n_slots]
+        hp = sl["hp"]
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(sl["free"])
+            for d, h in zip(hp.heads, host_sets[i % n_sets][0]):
+                d.copy_(h, non_blocking=True)
+            lab, n_gt, lb = label_sets[i % n_sets]
+            hp.labels.labels.copy_(lab, non_blocking=True)
+            hp.labels.n_gt.copy_(n_gt, non_blocking=True)
+            hp.labels.letterbox.copy_(lb, non_blocking=True)
+            sl["ready"].record(h2d_stream)
+
+    def compute(i):
+        sl = slots[i % n_slots]
+        hp = sl["hp"]
+        comp.wait_event(sl["ready"])
+        comp.wait_event(sl["rows_done"])
+        hp.replay()
+        sl["loss_host"].copy_(hp.losses, non_blocking=True)
+        sl["off_host"].copy_(hp.offsets, non_blocking=True)
+        sl["free"].record(comp)
+        sl["off_ready"].record(comp)
+
+    def collect(i):
+        sl = slots[i % n_slots]
+        sl["off_ready"].synchronize()
+        n = int(sl["off_host"][-1])
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(sl["off_ready"])
+            sl["det_host"][:n].copy_(sl["hp"].rows[:n], non_blocking=True)
+            sl["rows_done"].record(d2h_stream)
+        d2h_acc.append(16 + sl["off_host"].numel() * 4 + n * 24)
+
+    def run(n_steps):
+        enqueue_h2d(0)
+        if n_steps > 1:
+            enqueue_h2d(1)
+        compute(0)
+        for i in range(n_steps):
+            if i + 2 < n_steps:
+                enqueue_h2d(i + 2)
+            if i + 1 < n_steps:
+                compute(i + 1)
+            collect(i)
+        d2h_stream.synchronize()
+        comp.synchronize()
+
+    run(max(3, args.warmup))
+    d2h_acc.clear()
+    barrier()
+    t0 = time.perf_counter()
+    run(args.steps)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(wall_ms) / args.steps
+    return {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(np.mean(d2h_acc)),
+            "api": "HotPathGraph(targets='labels').replay(): loss fwd+bwd + detect + pack as one CUDA graph; pinned host "
+                   "heads + packed labels copied in, losses + detection rows copied out, 3 pipeline slots, host wall clock"}
 
 
 def run_torch_gpu_reference(args, dev, sample_images):

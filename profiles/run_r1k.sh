@@ -1,0 +1,2 @@
+set -x
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_k.log 2>&1; tail -5 gpurun_out/pytest_k.log

@@ -359,6 +359,46 @@ def test_nchw_heads_give_identical_results(yb, B, nc, grids, img):
             assert torch.equal(d0["keep"][b, :k], d1["keep"][b, :k])
 
 
+# ---- CUDA-graph step ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("targets,layout", [("labels", 0), ("dense", 0), ("labels", 1)])
+def test_hot_path_graph_replays_equal_eager(yb, targets, layout):
+    """The captured step (loss fwd+bwd + detect + pack) gives the eager results, replay after replay,
+    for new inputs copied into its static buffers."""
+    from yolo_from_scratch_b200 import ops
+    B, nc, img, grids = 3, 2, 160, (20, 10, 5)
+    hp = yb.HotPathGraph(B, img, nc, ANCH, conf_threshold=0.4, iou_threshold=0.4, max_gt=12, targets=targets,
+                         layout=layout)
+    for seed in (1, 2, 3):
+        g = torch.Generator().manual_seed(seed)
+        raw = [torch.randn(B, 3 * (5 + nc), G, G, generator=g).cuda() for G in grids]
+        heads = [yb.heads_from_nchw(r) for r in raw]
+        labels = _random_labels(np.random.default_rng(seed), B, nc, 12)
+        lab, n_gt, lb = ops.pack_labels_host(labels, img, max_gt=12)
+        for dst, src in zip(hp.heads, raw if layout else heads):
+            dst.copy_(src)
+        tg = yb.build_targets(labels, ANCH, list(grids), nc, img)
+        if targets == "labels":
+            hp.labels.labels.copy_(lab); hp.labels.n_gt.copy_(n_gt); hp.labels.letterbox.copy_(lb)
+        else:
+            for dst, src in zip(hp.targets, tg):
+                dst.copy_(src)
+        losses, grads, det = hp.replay()
+        ep = [h.clone().requires_grad_(True) for h in heads]
+        ref = yb.yolo_loss_multiscale(ep, tg, ANCH, nc)
+        ref[0].backward()
+        close(losses, torch.stack([r.detach() for r in ref]), rtol=1e-6, atol=1e-7)
+        back = (lambda t: yb.heads_from_nchw(t)) if layout else (lambda t: t)
+        for gph, e in zip(grads, ep):
+            close(back(gph), e.grad, rtol=1e-6, atol=1e-10)
+        d0 = yb.detect_batch(heads, ANCH, img, nc, 0.4, 0.4)
+        assert torch.equal(det["n_keep"], d0["n_keep"]) and torch.equal(det["counts"], d0["counts"])
+        for b in range(B):
+            k = int(d0["n_keep"][b])
+            assert torch.equal(det["keep"][b, :k], d0["keep"][b, :k])
+        rows0, off0 = yb.pack_detections(d0)
+        assert torch.equal(hp.offsets, off0) and torch.equal(hp.rows[:int(off0[-1])], rows0[:int(off0[-1])])
+
+
 # ---- eval_epoch counting (SURVEY 8f-1) -------------------------------------------------------------
 @pytest.mark.parametrize("name", ["e640", "e320"])
 def test_eval_epoch_matches_reference_golden(yb, golden, name):

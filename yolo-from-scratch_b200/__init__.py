@@ -10,7 +10,7 @@ from .ops import (batched_nms, batched_nms_padded, build_targets, ciou_loss, com
                   decode_predictions, detect_batch, detect_batch_nchw, detections_to_lists, heads_from_nchw, eval_counts, eval_epoch,
                   filter_candidates,
                   loss_forward_backward, nms, nms_retry_overflow, pack_detections,
-                  NMS_GRAPH, NMS_BITMASK, PackedLabels, pack_labels, pack_labels_host, yolo_loss,
+                  NMS_GRAPH, NMS_BITMASK, HotPathGraph, LAYOUT_BHWAC, LAYOUT_NCHW, PackedLabels, pack_labels, pack_labels_host, yolo_loss,
                   yolo_loss_multiscale, yolo_loss_multiscale_labels, yolo_loss_multiscale_nchw)
 
 __all__ = [
@@ -18,5 +18,5 @@ __all__ = [
     "build_targets", "filter_candidates", "nms", "batched_nms", "batched_nms_padded", "detect_batch",
     "detections_to_lists", "pack_detections", "loss_forward_backward", "yolo_loss_multiscale_labels",
     "PackedLabels", "pack_labels", "pack_labels_host", "eval_counts", "eval_epoch", "yolo_loss_multiscale_nchw",
-    "detect_batch_nchw", "heads_from_nchw",
+    "detect_batch_nchw", "heads_from_nchw", "HotPathGraph", "LAYOUT_BHWAC", "LAYOUT_NCHW",
 ]
