@@ -470,15 +470,20 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         nms_roof = {
             "kernel": "graph_edge_kernel", "bound": "fp32-issue", "unit": "Gpair/s", "peak": issue_peak,
             "peak_source": "148 SM x 4 schedulers x 32 lanes x sampled SM clock / 17 warp-instructions per 32 exact "
-                           "IoU>thr tests (SASS of the dense kernel)",
+                           "IoU>thr tests (SASS of the dense bitmask kernel): the rate at which ALL pairs could be tested",
+            # algorithmic work: the pairs torchvision's kernel evaluates, M(M-1)/2 per image
+            # (same-class pairs in the per-class regime), per launch, over the kernel's measured duration
             "algorithmic_pairs_per_launch": pairs,
+            "achieved": pairs / (ek["avg_ms"] * 1e-3) / 1e9,
+            "frac": pairs / (ek["avg_ms"] * 1e-3) / 1e9 / issue_peak,
+            "frac_note": "above 1 because the graph algorithm culls pairs by tile statistics instead of testing them",
+            # what the kernel really tests, and how much of the issue rate those tests use
             "evaluated_pairs_per_launch": evald,
             "edges_per_launch": float(np.mean(edge_counts)) if edge_counts else None,
-            # evaluated pair tests per second: how well the kernel uses the issue slots
-            "achieved": (evald / (ek["avg_ms"] * 1e-3) / 1e9) if evald else None,
-            "frac": (evald / (ek["avg_ms"] * 1e-3) / 1e9 / issue_peak) if evald else None,
-            # all pairs torchvision's kernel would evaluate, per second of the whole NMS (sort+edges+resolve)
-            "effective_algorithmic_gpairs": pairs / (nms_ms * 1e-3) / 1e9 if nms_ms else None,
+            "evaluated_gpairs": (evald / (ek["avg_ms"] * 1e-3) / 1e9) if evald else None,
+            "evaluated_frac_of_peak": (evald / (ek["avg_ms"] * 1e-3) / 1e9 / issue_peak) if evald else None,
+            # all algorithmic pairs per second of the whole NMS (sort + gather + edges + resolve)
+            "whole_nms_algorithmic_gpairs": pairs / (nms_ms * 1e-3) / 1e9 if nms_ms else None,
             "share": ek["share"], "traffic": traffic.get("graph_edge_kernel"),
         }
     dominant = max(kernels, key=lambda k: kernels[k]["share"]) if kernels else None

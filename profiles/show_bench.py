@@ -9,7 +9,7 @@ print({k: d.get(k) for k in ['value', 'ms_per_step', 'loss_fwd_bwd_ms', 'decode_
 print('e2e', d.get('e2e'))
 print(kern(d))
 r = d.get('roofline') or {}
-print('roofline', {k: r.get(k) for k in ['kernel', 'bound', 'achieved', 'peak', 'frac', 'share', 'evaluated_pairs_per_launch', 'effective_algorithmic_gpairs']})
+print('roofline', {k: r.get(k) for k in ['kernel', 'bound', 'achieved', 'peak', 'frac', 'share', 'evaluated_pairs_per_launch', 'evaluated_frac_of_peak', 'whole_nms_algorithmic_gpairs']})
 print('hbm', {k: (round(v['achieved']), round(v['frac'], 3)) for k, v in (d.get('hbm_kernels') or {}).items()})
 for k in ('cpu_baseline', 'torch_gpu_baseline', 'variants', 'clocks'):
     if d.get(k):

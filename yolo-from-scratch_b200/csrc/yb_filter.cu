@@ -108,22 +108,25 @@ __global__ void __launch_bounds__(kFTile) filter_count_kernel(const FilterArgs a
 // divergent sigmoid re-evaluations).
 template <typename Load>
 __device__ __forceinline__ void class_max(int nc, Load ld, float& prob, int& id) {
-    float m = ld(0);
+    // one pass: maximum m, its first index mi, and the runner-up m2 (largest value at any other index)
+    float m = ld(0), m2 = -INFINITY;
     int mi = 0, c = 1;
-    for (; c + 4 <= nc; c += 4) {  // 4 independent loads per step
-        const float v0 = ld(c), v1 = ld(c + 1), v2 = ld(c + 2), v3 = ld(c + 3);
-        if (v0 > m) { m = v0; mi = c; }
-        if (v1 > m) { m = v1; mi = c + 1; }
-        if (v2 > m) { m = v2; mi = c + 2; }
-        if (v3 > m) { m = v3; mi = c + 3; }
+    auto step = [&](float v, int idx) {
+        if (v > m) { m2 = m; m = v; mi = idx; }
+        else m2 = v > m2 ? v : m2;
+    };
+    for (; c + 8 <= nc; c += 8) {  // 8 independent loads per step
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ld(c + k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) step(v[k], c + k);
     }
-    for (; c < nc; ++c) {
-        const float v = ld(c);
-        if (v > m) { m = v; mi = c; }
-    }
+    for (; c < nc; ++c) step(ld(c), c);
     prob = sigmoidf_ref(m);
     id = mi;
     const float lo = (m <= 14.0f) ? m - 2e-6f * (1.0f + expf(m)) : 13.0f;
+    if (!(m2 > lo)) return;  // nothing else is close enough to round to the same probability
     for (c = 0; c < nc; ++c) {  // near-ties on either side of mi (expf need not be monotone to the last ulp)
         const float v = ld(c);
         if (v > lo && c != mi) {
@@ -292,6 +295,145 @@ __global__ void __launch_bounds__(kFTile) filter_emit_kernel(const FilterArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// NCHW heads (f-2): (B, A*row, H, W), the head conv's own output.  A tile is 128 consecutive CELLS of
+// one scale with all A anchors (128*A canonical rows): thread <-> cell, so every load of a channel
+// plane is a fully coalesced 128-byte line per warp and no shared-memory staging is needed.  The
+// candidate order stays the canonical (cell, anchor) order of the reference layout.
+// ------------------------------------------------------------------------------------------------
+struct FilterNchw {
+    uint32_t tile_begin[YB_MAX_SCALES];  // first cell tile (within an image) of each scale
+    uint32_t tiles_per_img;
+};
+
+__device__ __forceinline__ int nchw_tile_scale(const FilterArgs& a, const FilterNchw& n, uint32_t tile) {
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < YB_MAX_SCALES; ++k)
+        if (k < a.S && tile >= n.tile_begin[k]) s = k;
+    return s;
+}
+
+__global__ void __launch_bounds__(kFTile) filter_count_nchw_kernel(const FilterArgs a, const FilterNchw n) {
+    __shared__ int s_red[kFTile / 32];
+    const uint32_t tile = blockIdx.x, b = blockIdx.y;
+    const int s = nchw_tile_scale(a, n, tile);
+    const FilterScale& L = a.sc[s];
+    const uint32_t cell = (tile - n.tile_begin[s]) * kFTile + threadIdx.x;
+    int cnt = 0;
+    if (cell < L.hw) {
+        float x[YB_MAX_ANCHORS];
+#pragma unroll
+        for (int an = 0; an < YB_MAX_ANCHORS; ++an)
+            if (an < a.A) x[an] = __ldg(L.pred + ((size_t)(b * (uint32_t)a.A + an) * a.row + 4) * L.hw + cell);
+#pragma unroll
+        for (int an = 0; an < YB_MAX_ANCHORS; ++an)
+            if (an < a.A) cnt += sigmoidf_ref(x[an]) > a.conf ? 1 : 0;  // :1157,:1166-1167 objectness only
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < kFTile / 32; ++k) tot += s_red[k];
+        a.tile_counts[b * n.tiles_per_img + tile] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(kFTile) filter_emit_nchw_kernel(const FilterArgs a, const FilterNchw n) {
+    __shared__ int s_red[kFTile / 32];
+    __shared__ int s_wsum[kFTile / 32];
+    const uint32_t tile = blockIdx.x, b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int* tc = a.tile_counts + b * n.tiles_per_img;
+    int part = 0;
+    for (uint32_t t = threadIdx.x; t < tile; t += kFTile) part += tc[t];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    int prefix = 0;
+#pragma unroll
+    for (int k = 0; k < kFTile / 32; ++k) prefix += s_red[k];
+    const int count = tc[tile];
+    if (tile == n.tiles_per_img - 1 && threadIdx.x == 0) {
+        const int tot = prefix + count;
+        a.counts[b] = tot < a.cap ? tot : a.cap;
+    }
+    if (count == 0) return;
+
+    const int s = nchw_tile_scale(a, n, tile);
+    const FilterScale& L = a.sc[s];
+    const uint32_t cell = (tile - n.tile_begin[s]) * kFTile + threadIdx.x;
+    const bool valid = cell < L.hw;
+    const float* plane0 = L.pred + (size_t)b * a.A * a.row * L.hw + (valid ? cell : 0u);  // channel 0, anchor 0
+    const size_t hw = L.hw;
+
+    // phase A: objectness of this cell for every anchor
+    float so[YB_MAX_ANCHORS];
+    unsigned passmask = 0u;
+#pragma unroll
+    for (int an = 0; an < YB_MAX_ANCHORS; ++an) {
+        so[an] = 0.0f;
+        if (an < a.A && valid) so[an] = __ldg(plane0 + ((size_t)an * a.row + 4) * hw);
+    }
+#pragma unroll
+    for (int an = 0; an < YB_MAX_ANCHORS; ++an) {
+        if (an < a.A && valid) {
+            so[an] = sigmoidf_ref(so[an]);
+            if (so[an] > a.conf) passmask |= 1u << an;
+        }
+    }
+    // exclusive scan of the per-cell pass counts: canonical order is (cell, anchor)
+    const int mine = __popc(passmask);
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    int pos = prefix + inc - mine;
+    for (int k = 0; k < warp; ++k) pos += s_wsum[k];
+    if (!passmask) return;
+
+    float inv_s = 1.0f, pt = 0.0f, pl = 0.0f;
+    if (a.letterbox) {
+        inv_s = 1.0f / a.letterbox[b * 3 + 0];
+        pt = a.letterbox[b * 3 + 1];
+        pl = a.letterbox[b * 3 + 2];
+    }
+    uint32_t gy, gx;
+    L.d_W.divmod(cell, gy, gx);
+#pragma unroll
+    for (int an = 0; an < YB_MAX_ANCHORS; ++an) {
+        if (an >= a.A || !((passmask >> an) & 1u)) continue;
+        if (pos >= a.cap) break;
+        const float* x = plane0 + (size_t)an * a.row * hw;
+        const float aw = __ldg(L.anchors + an * 2), ah = __ldg(L.anchors + an * 2 + 1);
+        const float x0 = __ldg(x), x1r = __ldg(x + hw), x2r = __ldg(x + 2 * hw), x3r = __ldg(x + 3 * hw);
+        float cprob;
+        int cid;
+        class_max(a.nc, [&](int c) { return __ldg(x + (size_t)(5 + c) * hw); }, cprob, cid);
+        const float bx = decode_xy(x0, (float)gx, L.inv_w);
+        const float by = decode_xy(x1r, (float)gy, L.inv_h);
+        const float bw = decode_wh(x2r, aw, a.inv_img);
+        const float bh = decode_wh(x3r, ah, a.inv_img);
+        const float xc = bx * a.img, yc = by * a.img, wp = bw * a.img, hp = bh * a.img;
+        float x1 = xc - wp * 0.5f, y1 = yc - hp * 0.5f, x2 = xc + wp * 0.5f, y2 = yc + hp * 0.5f;
+        if (a.letterbox) {
+            x1 = (x1 - pl) * inv_s; y1 = (y1 - pt) * inv_s;
+            x2 = (x2 - pl) * inv_s; y2 = (y2 - pt) * inv_s;
+        }
+        const size_t o = (size_t)b * a.cap + pos;
+        a.boxes[o] = make_float4(x1, y1, x2, y2);
+        a.scores[o] = so[an] * cprob;
+        a.classes[o] = (int64_t)cid;
+        ++pos;
+    }
+}
+
 static int filter_fill(const yb_heads_desc* d, FilterArgs& a) {
     YB_CHECK_ARG(d, "filter: null descriptor");
     YB_CHECK_ARG(d->S >= 1 && d->S <= YB_MAX_SCALES && d->B >= 0 && d->A > 0 && d->A <= YB_MAX_ANCHORS && d->nc >= 1,
@@ -363,6 +505,19 @@ extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const
     a.sobj_offset = (uint32_t)(smem / sizeof(float));
     smem += (size_t)a.G * kFTile * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    if (a.nchw) {
+        FilterNchw n;
+        uint32_t t = 0;
+        for (int s = 0; s < d->S; ++s) {
+            n.tile_begin[s] = t;
+            t += (a.sc[s].hw + kFTile - 1) / kFTile;
+        }
+        n.tiles_per_img = t;  // <= tiles_per_img of the row tiling: the workspace is large enough
+        dim3 ngrid(t, d->B);
+        YB_LAUNCH("filter_count_nchw_kernel", st, filter_count_nchw_kernel<<<ngrid, kFTile, 0, st>>>(a, n));
+        YB_LAUNCH("filter_emit_nchw_kernel", st, filter_emit_nchw_kernel<<<ngrid, kFTile, 0, st>>>(a, n));
+        return 0;
+    }
     dim3 grid(a.groups_per_img, d->B);
     YB_LAUNCH("filter_count_kernel", st, filter_count_kernel<<<grid, kFTile, 0, st>>>(a));
     const size_t dyn = smem;

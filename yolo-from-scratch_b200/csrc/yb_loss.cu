@@ -292,12 +292,31 @@ __global__ void __launch_bounds__(kTileRows) loss_main_kernel(const LossArgs a) 
 // read of the logits (4 bytes per row instead of one 128-byte DRAM line per row in the reference
 // layout), the targets' objectness (dense: reference layout; sparse: the bit map) and a coalesced
 // store of the gradient.
+constexpr int kNchwVecs = 4;  // float4 vectors per thread and tile: 256 threads x 4 x 16 B = 16 KB per tile
+
+template <bool SPARSE>
+__device__ __forceinline__ float nchw_obj_elem(const LossArgs& a, const LossScale& L, int s, uint32_t ba, uint32_t cell,
+                                               float x, float& bce) {
+    uint32_t b, an;
+    L.d_A.divmod(ba, b, an);
+    const uint32_t r = (b * L.HW + cell) * (uint32_t)a.A + an;  // canonical row
+    float t;
+    if (SPARSE) t = ((__ldg(L.bits + (r >> 5)) >> (r & 31)) & 1u) ? 1.0f : 0.0f;
+    else t = __ldg(L.tgt + (size_t)r * a.row + 4);
+    bce += bce_logits_ref(x, t);
+    if (!SPARSE && t > 0.5f) {
+        const int slot = atomicAdd(a.pos_count + s, 1);
+        a.pos_list[L.list_begin + slot] = r;
+    }
+    return (sigmoidf_ref(x) - t) * L.obj_scale;
+}
+
 template <bool SPARSE>
 __global__ void __launch_bounds__(kTileRows) loss_main_nchw_kernel(const LossArgs a) {
-    __shared__ float s_warp[kTileRows / 32];
-    double cta_sum[YB_MAX_SCALES];
+    __shared__ double s_part[kTileRows / 32][YB_MAX_SCALES];
+    double acc[YB_MAX_SCALES];
 #pragma unroll
-    for (int s = 0; s < YB_MAX_SCALES; ++s) cta_sum[s] = 0.0;
+    for (int s = 0; s < YB_MAX_SCALES; ++s) acc[s] = 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -306,61 +325,51 @@ __global__ void __launch_bounds__(kTileRows) loss_main_nchw_kernel(const LossArg
         for (int k = 1; k < YB_MAX_SCALES; ++k)
             if (k < a.S && tile >= a.sc[k].tile_begin) s = k;
         const LossScale& L = a.sc[s];
-        const uint32_t e0 = ((tile - L.tile_begin) * kTileRows + threadIdx.x) * 4u;  // first float of this thread
         float bce = 0.0f;
-        if (e0 < L.n_float) {
+#pragma unroll
+        for (int k = 0; k < kNchwVecs; ++k) {
+            const uint32_t e0 = (((tile - L.tile_begin) * kNchwVecs + k) * kTileRows + threadIdx.x) * 4u;
+            if (e0 >= L.n_float) continue;
             uint32_t plane, within;
             L.d_HW.divmod(e0, plane, within);
             float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t e = e0 + k;
-                if (e < L.n_float) {
+            if (within + 4u <= L.HW && e0 + 4u <= L.n_float) {  // the common case: one channel plane
+                uint32_t ba, c;
+                a.d_row.divmod(plane, ba, c);
+                if (c == 4u) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(L.pred + e0));
+                    o[0] = nchw_obj_elem<SPARSE>(a, L, s, ba, within, x.x, bce);
+                    o[1] = nchw_obj_elem<SPARSE>(a, L, s, ba, within + 1, x.y, bce);
+                    o[2] = nchw_obj_elem<SPARSE>(a, L, s, ba, within + 2, x.z, bce);
+                    o[3] = nchw_obj_elem<SPARSE>(a, L, s, ba, within + 3, x.w, bce);
+                }
+                if (L.grad) *reinterpret_cast<float4*>(L.grad + e0) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {  // a vector straddling two planes or the end of the tensor (H*W not a multiple of 4)
+                for (uint32_t j = 0; j < 4u && e0 + j < L.n_float; ++j) {
                     uint32_t ba, c;
                     a.d_row.divmod(plane, ba, c);
-                    if (c == 4u) {
-                        uint32_t b, an;
-                        L.d_A.divmod(ba, b, an);
-                        const uint32_t r = (b * L.HW + within) * (uint32_t)a.A + an;  // canonical row
-                        const float x = __ldg(L.pred + e);
-                        float t;
-                        if (SPARSE) t = ((__ldg(L.bits + (r >> 5)) >> (r & 31)) & 1u) ? 1.0f : 0.0f;
-                        else t = __ldg(L.tgt + (size_t)r * a.row + 4);
-                        bce += bce_logits_ref(x, t);
-                        o[k] = (sigmoidf_ref(x) - t) * L.obj_scale;
-                        if (!SPARSE && t > 0.5f) {
-                            const int slot = atomicAdd(a.pos_count + s, 1);
-                            a.pos_list[L.list_begin + slot] = r;
-                        }
-                    }
-                }
-                if (++within == L.HW) { within = 0; ++plane; }
-            }
-            if (L.grad) {
-                if (e0 + 4u <= L.n_float) {
-                    *reinterpret_cast<float4*>(L.grad + e0) = make_float4(o[0], o[1], o[2], o[3]);
-                } else {
-                    for (uint32_t k = 0; e0 + k < L.n_float; ++k) L.grad[e0 + k] = o[k];
+                    float v = 0.0f;
+                    if (c == 4u) v = nchw_obj_elem<SPARSE>(a, L, s, ba, within, __ldg(L.pred + e0 + j), bce);
+                    if (L.grad) L.grad[e0 + j] = v;
+                    if (++within == L.HW) { within = 0; ++plane; }
                 }
             }
         }
-        const float wsum = warp_sum(bce);
-        if (lane == 0) s_warp[warp] = wsum;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float tsum = 0.0f;
 #pragma unroll
-            for (int k = 0; k < kTileRows / 32; ++k) tsum += s_warp[k];
-#pragma unroll
-            for (int k = 0; k < YB_MAX_SCALES; ++k)
-                if (k == s) cta_sum[k] += (double)tsum;
-        }
-        __syncthreads();
+        for (int k = 0; k < YB_MAX_SCALES; ++k)
+            if (k == s) acc[k] += (double)bce;
     }
-    if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < YB_MAX_SCALES; ++s)
-            if (s < a.S && cta_sum[s] != 0.0) atomicAdd(a.partials + s * 4 + 2, cta_sum[s]);
+    for (int s = 0; s < YB_MAX_SCALES; ++s) {
+        const double w = warp_sum(acc[s]);
+        if (lane == 0) s_part[warp][s] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < YB_MAX_SCALES && (int)threadIdx.x < a.S) {
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < kTileRows / 32; ++k) tot += s_part[k][threadIdx.x];
+        if (tot != 0.0) atomicAdd(a.partials + threadIdx.x * 4 + 2, tot);
     }
 }
 
@@ -537,8 +546,9 @@ static void loss_fill_args(const yb_loss_desc* d, void* ws, LossArgs& a) {
         L.HW = (uint32_t)d->H[s] * (uint32_t)d->W[s];
         L.n_float = L.rows * a.row;
         L.d_HW = FastDiv(L.HW);
-        // reference layout: one tile = kTileRows rows; NCHW: one tile = kTileRows float4 of the flat tensor
-        tile += a.nchw ? (L.n_float + kTileRows * 4 - 1) / (kTileRows * 4) : (L.rows + kTileRows - 1) / kTileRows;
+        // reference layout: one tile = kTileRows rows; NCHW: one tile = kTileRows*kNchwVecs float4 of the flat tensor
+        tile += a.nchw ? (L.n_float + kTileRows * 4 * kNchwVecs - 1) / (kTileRows * 4 * kNchwVecs)
+                       : (L.rows + kTileRows - 1) / kTileRows;
         list += L.rows;
         L.H = d->H[s]; L.W = d->W[s];
         L.inv_w = 1.0f / (float)d->W[s]; L.inv_h = 1.0f / (float)d->H[s];
