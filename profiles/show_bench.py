@@ -7,6 +7,9 @@ def kern(o):
     return {k: (round(v['avg_ms'] * 1e3, 1), round(v['share'], 3)) for k, v in o['kernels'].items()}
 print({k: d.get(k) for k in ['value', 'ms_per_step', 'loss_fwd_bwd_ms', 'decode_nms_ms', 'n_gpus']})
 print('e2e', d.get('e2e'))
+for k in ('e2e_labels', 'e2e_graph', 'graph_replay'):
+    if d.get(k):
+        print(k, {q: d[k].get(q) for q in ('value', 'ms_per_step')})
 print(kern(d))
 r = d.get('roofline') or {}
 print('roofline', {k: r.get(k) for k in ['kernel', 'bound', 'achieved', 'peak', 'frac', 'share', 'evaluated_pairs_per_launch', 'evaluated_frac_of_peak', 'whole_nms_algorithmic_gpairs']})

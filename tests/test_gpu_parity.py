@@ -399,6 +399,30 @@ def test_hot_path_graph_replays_equal_eager(yb, targets, layout):
         assert torch.equal(hp.offsets, off0) and torch.equal(hp.rows[:int(off0[-1])], rows0[:int(off0[-1])])
 
 
+def test_nchw_filter_sparse_empty_and_letterbox(yb):
+    """NCHW filter edge cases: letterbox reverse, a threshold nothing passes, a threshold a few rows pass
+    (sparse tiles), images with no candidate at all; all equal to the reference-layout kernels."""
+    nc, img, grids, B = 3, 256, (32, 16, 8), 4
+    g = torch.Generator().manual_seed(77)
+    raw = [torch.randn(B, 3 * (5 + nc), G, G, generator=g).cuda() for G in grids]
+    for r in raw:
+        r[1, 4::(5 + nc)] = -20.0          # image 1: objectness off everywhere
+    heads = [yb.heads_from_nchw(r) for r in raw]
+    lb = [(0.5, 10.0, 0.0), (1.0, 0.0, 0.0), (0.8, 0.0, 25.6), (0.3, 3.0, 4.0)]
+    for conf in (0.9999999, 0.98, 0.5):
+        d0 = yb.detect_batch(heads, ANCH, img, nc, conf, 0.4, letterbox=lb)
+        d1 = yb.detect_batch_nchw(raw, ANCH, img, nc, conf, 0.4, letterbox=lb)
+        assert torch.equal(d0["counts"], d1["counts"]) and int(d0["counts"][1]) == 0
+        assert torch.equal(d0["n_keep"], d1["n_keep"])
+        for b in range(B):
+            m, k = int(d0["counts"][b]), int(d0["n_keep"][b])
+            assert torch.equal(d0["boxes"][b, :m], d1["boxes"][b, :m])
+            assert torch.equal(d0["scores"][b, :m], d1["scores"][b, :m])
+            assert torch.equal(d0["classes"][b, :m], d1["classes"][b, :m])
+            assert torch.equal(d0["keep"][b, :k], d1["keep"][b, :k])
+    assert int(yb.detect_batch_nchw(raw, ANCH, img, nc, 0.9999999, 0.4)["counts"].sum()) == 0
+
+
 # ---- eval_epoch counting (SURVEY 8f-1) -------------------------------------------------------------
 @pytest.mark.parametrize("name", ["e640", "e320"])
 def test_eval_epoch_matches_reference_golden(yb, golden, name):

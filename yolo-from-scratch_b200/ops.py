@@ -789,7 +789,10 @@ class HotPathGraph:
     Images whose NMS graph overflowed report det["n_keep"] < 0, as with detect_batch."""
 
     def __init__(self, batch, img_size, num_classes, anchors_list, conf_threshold=0.5, iou_threshold=0.4, max_gt=50,
-                 targets="labels", layout=LAYOUT_BHWAC, num_anchors=3, device=None):
+                 targets="labels", layout=LAYOUT_BHWAC, num_anchors=3, device=None, adopt_heads=None,
+                 adopt_targets=None):
+        """adopt_heads / adopt_targets: existing device tensors (or a PackedLabels) to use as the static
+        inputs instead of allocating new ones."""
         dev = _device() if device is None else torch.device(device)
         self.device, self.nc, self.img, self.layout = dev, int(num_classes), int(img_size), layout
         row = 5 + self.nc
@@ -797,12 +800,19 @@ class HotPathGraph:
         with torch.cuda.device(dev):
             self.anchors = [_anchors_dev(a, dev) for a in anchors_list]
             A = num_anchors
-            if layout == LAYOUT_NCHW:
+            if adopt_heads is not None:
+                self.heads = list(adopt_heads)
+            elif layout == LAYOUT_NCHW:
                 self.heads = [torch.zeros(batch, A * row, g, g, device=dev) for g in grids]
             else:
                 self.heads = [torch.zeros(batch, g, g, A, row, device=dev) for g in grids]
             self.labels = self.targets = None
-            if targets == "labels":
+            if adopt_targets is not None:
+                if isinstance(adopt_targets, PackedLabels):
+                    self.labels = adopt_targets
+                else:
+                    self.targets = list(adopt_targets)
+            elif targets == "labels":
                 self.labels = PackedLabels(torch.zeros(batch, max(max_gt, 1), 5, dtype=torch.float64, device=dev),
                                            torch.zeros(batch, dtype=torch.int32, device=dev),
                                            torch.tensor([[img_size, img_size, 1.0, 0.0, 0.0]] * batch, dtype=torch.float64,
