@@ -225,8 +225,7 @@ int yb_batched_nms(const float* boxes, const float* scores, const int64_t* class
                    void* ws, size_t ws_bytes, void* stream);
 
 /* Statistics of the last YB_NMS_GRAPH call that used workspace `ws` (bench/tests; synchronises the
- * stream): pair-test evaluations in units of 8 pairs (one row against an 8-column sub-tile) and edges
- * found, summed over the B images.  Outputs are HOST pointers (nullable). */
+ * stream): IoU pair tests executed and edges found, summed over the B images.  Outputs are HOST pointers (nullable). */
 int yb_nms_graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned long long* evals_host,
                        unsigned long long* edges_host, void* stream);
 

@@ -8,6 +8,7 @@ import subprocess
 import sys
 import types
 
+import numpy as np
 import pytest
 import torch
 
@@ -159,3 +160,56 @@ def test_install_on_live_reference(yb, reference_module):
             assert [p.default for p in a.parameters.values()] == [p.default for p in b.parameters.values()], n
     finally:
         inst.uninstall(ref)
+
+
+def test_eval_epoch_is_rebound_and_restored(yb):
+    from yolo_from_scratch_b200 import install as inst, ops
+    m, _ = fake_train_module()
+    m.eval_epoch = lambda model, loader, device, num_classes=1, iou_threshold=0.5, conf_threshold=0.5: "ref"
+    orig = m.eval_epoch
+    inst.install(m)
+    try:
+        assert m.eval_epoch is ops.eval_epoch
+    finally:
+        inst.uninstall(m)
+    assert m.eval_epoch is orig
+    m2, _ = fake_train_module()
+    m2.eval_epoch = orig
+    inst.install(m2, patch_eval=False)
+    try:
+        assert m2.eval_epoch is orig
+    finally:
+        inst.uninstall(m2)
+
+
+def test_eval_epoch_signature_matches_reference(yb, reference_module):
+    import inspect
+    from yolo_from_scratch_b200 import ops
+    assert str(inspect.signature(ops.eval_epoch)) == str(inspect.signature(reference_module.eval_epoch))
+
+
+def test_label_packing_and_layout_helpers_on_cpu(yb):
+    """Host-side helpers of the f-2 / f-4 entry points need no GPU."""
+    from yolo_from_scratch_b200 import ops
+    labels = [np.array([[1, .5, .5, .2, .3], [0, .1, .2, .05, .05]]), np.zeros((0, 5)), np.array([[2, .9, .9, .1, .1]])]
+    lab, n_gt, lb = ops.pack_labels_host(labels, 320)
+    assert lab.shape == (3, 2, 5) and lab.dtype == torch.float64 and n_gt.tolist() == [2, 0, 1]
+    assert lb.tolist() == [[320.0, 320.0, 1.0, 0.0, 0.0]] * 3
+    assert float(lab[2, 0, 1]) == 0.9 and float(lab[1].abs().sum()) == 0.0
+    lab, n_gt, lb = ops.pack_labels_host(labels, 320, letterbox=[(500, 375, 0.64, 40, 0)] * 3, max_gt=7)
+    assert lab.shape == (3, 7, 5) and lb[0].tolist() == [500.0, 375.0, 0.64, 40.0, 0.0]
+    with pytest.raises(ValueError):
+        ops.pack_labels_host(labels, 320, max_gt=1)
+    assert ops.pack_labels_host([], 320)[0].shape == (0, 1, 5)
+    # heads_from_nchw is exactly the reference's reshape (train.py:608-609)
+    B, A, nc, G = 2, 3, 4, 5
+    raw = torch.arange(B * A * (5 + nc) * G * G, dtype=torch.float32).reshape(B, A * (5 + nc), G, G)
+    want = raw.view(B, A, 5 + nc, G, G).permute(0, 3, 4, 1, 2).contiguous()
+    got = ops.heads_from_nchw(raw, A)
+    assert got.shape == (B, G, G, A, 5 + nc) and got.is_contiguous() and torch.equal(got, want)
+    assert float(got[1, 2, 3, 1, 4]) == float(raw[1, 1 * (5 + nc) + 4, 2, 3])
+
+
+def test_desc_layout_field_defaults_to_reference_layout(yb):
+    L, H = yb._lib.LossDesc(), yb._lib.HeadsDesc()
+    assert L.layout == yb._lib.LAYOUT_BHWAC == 0 and H.layout == 0 and yb._lib.LAYOUT_NCHW == 1

@@ -12,13 +12,17 @@
 //      result is the unique fixed point of  "kept <=> every higher-scored neighbour is
 //      suppressed; suppressed <=> some higher-scored neighbour is kept", reached by parallel
 //      rounds (8 rounds on 25,200 random boxes).
-// Three launches for a whole batch:
-//   graph_sort_kernel     one CTA per image: stable score sort (rank), spatial sort (position),
-//                         gather of (offset) boxes, per-tile bounding statistics
-//   graph_edge_kernel     persistent warps, one row tile at a time: tile-pair culling, row culling,
-//                         IoU > thr decided with the division-free margin test (ambiguous lanes
-//                         redo torchvision's exact fma/div arithmetic with the higher-scored box
-//                         as `a`), warp-aggregated append of directed edges (rank_hi -> rank_lo)
+// Four launches for a whole batch:
+//   graph_sort_kernel     two CTAs per image: stable score order (rank <-> index maps) and spatial
+//                         order, each by a shared-memory blocked radix sort (yb_sort.cuh)
+//   graph_gather_kernel   boxes / rank / class in position order (coordinate-offset trick applied),
+//                         bounding statistics per 32-box tile and per 8-box sub-tile
+//   graph_edge_kernel     persistent warps, one row tile at a time, three culling levels (tile,
+//                         sub-tile, row vs sub-tile), surviving (row, sub-tile) items packed so that
+//                         every pair-loop iteration tests 4 items x 8 columns on all 32 lanes;
+//                         IoU > thr decided with the division-free margin test (ambiguous lanes redo
+//                         torchvision's exact fma/div arithmetic with the higher-scored box as `a`);
+//                         edges (rank_hi -> rank_lo) buffered per warp, one atomic per 33..64 edges
 //   graph_resolve_kernel  one CTA per image: fixed-point rounds over the edge list in shared-memory
 //                         bitmaps, then ordered emission of the kept indices by score rank
 // Bound: fp32 SIMT issue on the pair evaluations that survive culling.
@@ -29,7 +33,8 @@
 namespace yb {
 
 constexpr int kTile = 32;
-constexpr int kSub = 8;             // columns per sub-tile (row culling granularity)
+constexpr int kSub = 8;             // columns per sub-tile (row culling granularity); 4 halves the pair tests
+                                    // (46 M vs 84 M on configs[1]) but doubles the per-chunk tests: 524 vs 381 us
 constexpr int kSubs = kTile / kSub;
 constexpr uint32_t kNoSub = 0xffffffffu;
 constexpr int kGatherThreads = 256;
@@ -43,7 +48,7 @@ struct GImg {
     int n_tiles;
     u32 n_edges;
     float s_off, t2;  // coordinate offset step; pruning threshold thr*(1-2^-10) (or -1: no pruning)
-    unsigned long long n_evals;  // statistics: row-vs-8-columns evaluations (8 pair tests each)
+    unsigned long long n_evals;  // statistics: (row, sub-tile) items evaluated (kSub pair tests each)
 };
 
 struct GArgs {
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
         c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
         c1 = max(c1, __shfl_xor_sync(0xffffffffu, c1, o));
-        if (o == kSub / 2 && (lane & (kSub - 1)) == 0) {  // statistics of this lane's 8-box sub-tile
+        if (o == kSub / 2 && (lane & (kSub - 1)) == 0) {  // statistics of this lane's kSub-box sub-tile
             float4* ss = a.sstat + (((size_t)b * a.tcap + t) * kSubs + (lane / kSub)) * 2;
             ss[0] = make_float4(x1, y1, x2, y2);
             ss[1] = make_float4(amin, amax, 0.0f, 0.0f);
@@ -293,7 +298,24 @@ struct EdgeWarp {
     u32 tl[kTile];          // compaction scratch: surviving tiles of the current step
     u32 sub[kTile * kSubs + 8];  // queue of surviving sub-tile ids (J*kSubs+s); < 4 left over between steps
     unsigned char item[kTile * kSubs];  // (sub-tile slot << 5) | row, packed work list of a chunk
+    uint2 ebuf[2 * kTile];  // edges found, flushed to the image's list 33..64 at a time (one atomic per flush)
 };
+
+// Append the warp's buffered edges to image b's list.
+__device__ __forceinline__ void edge_flush(const GArgs& a, EdgeWarp& w, int b, uint2* __restrict__ edges, int& n_buf) {
+    if (n_buf == 0) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(&a.info[b].n_edges, (u32)n_buf);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int k = lane; k < n_buf; k += 32) {
+        const u64 idx = (u64)base + k;
+        if (idx < a.edges_per_img) edges[idx] = w.ebuf[k];
+    }
+    __syncwarp();
+    n_buf = 0;
+}
 
 // One chunk = up to 4 sub-tiles (8 columns each) that survived the tile-level tests against row
 // tile I.  Lane l holds column (l&7) of slot (l>>3).  Rows are culled against each slot's
@@ -304,7 +326,7 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
                                            const u32* __restrict__ scls, const float4* __restrict__ ss,
                                            uint2* __restrict__ edges, const float4 rq, const bool rvalid,
                                            const float rw_t, const float rh_t, const float rS, const float rS_t,
-                                           u32& n_evals) {
+                                           u32& n_evals, int& n_buf) {
     const int lane = threadIdx.x & 31;
     const int grp = lane / kSub;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -394,14 +416,9 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
         const bool fin = pr && qvalid && (!class_mode || ccls == ra.cls) && qp > I * kTile + i;
         const unsigned em = __ballot_sync(0xffffffffu, fin);
         if (em) {
-            const int leader = __ffs(em) - 1;
-            u32 base = 0;
-            if (lane == leader) base = atomicAdd(&a.info[b].n_edges, (u32)__popc(em));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (fin) {
-                const u64 k = (u64)base + __popc(em & lt_mask);
-                if (k < a.edges_per_img) edges[k] = make_uint2(min(ra.rank, crank), max(ra.rank, crank));
-            }
+            if (fin) w.ebuf[n_buf + __popc(em & lt_mask)] = make_uint2(min(ra.rank, crank), max(ra.rank, crank));
+            n_buf += __popc(em);
+            if (n_buf > kTile) edge_flush(a, w, b, edges, n_buf);  // no room for another 32
         }
     }
     __syncwarp();
@@ -450,7 +467,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
         const u32 icmin = __float_as_uint(ia.z), icmax = __float_as_uint(ia.w);
         u32 n_evals = 0;
-        int n_q = 0;  // sub-tiles waiting in w.sub
+        int n_q = 0;    // sub-tiles waiting in w.sub
+        int n_buf = 0;  // edges waiting in w.ebuf
 
         for (int J0 = I;; J0 += 32) {
             const bool tail = J0 >= info.n_tiles;  // one extra round flushes the last partial chunk
@@ -506,7 +524,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
             // level 3: chunks of 4 sub-tiles
             int head = 0;
             for (; n_q - head >= kSubs; head += kSubs)
-                edge_chunk(a, w, info, b, I, head, sb, srank, scls, ss, edges, rq, rvalid, rw_t, rh_t, rS, rS_t, n_evals);
+                edge_chunk(a, w, info, b, I, head, sb, srank, scls, ss, edges, rq, rvalid, rw_t, rh_t, rS, rS_t, n_evals,
+                           n_buf);
             if (head) {  // move the < 4 leftovers to the front
                 const int rem = n_q - head;
                 u32 v = 0u;
@@ -517,6 +536,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                 n_q = rem;
             }
         }
+        edge_flush(a, w, b, edges, n_buf);
         if (lane == 0 && n_evals) atomicAdd(&a.info[b].n_evals, (unsigned long long)n_evals);
     }
 }
@@ -691,7 +711,7 @@ int graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned long l
                             cudaMemcpyDeviceToHost, st));
     YB_CUDA(cudaStreamSynchronize(st));
     unsigned long long ev = 0, ed = 0;
-    for (auto& g : h) { ev += g.n_evals; ed += g.n_edges; }
+    for (auto& g : h) { ev += g.n_evals * (unsigned long long)kSub; ed += g.n_edges; }  // items -> pair tests
     if (evals) *evals = ev;
     if (edges) *edges = ed;
     return 0;

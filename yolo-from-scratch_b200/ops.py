@@ -656,7 +656,7 @@ def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_
 
 
 def nms_graph_stats(det):
-    """(8-pair evaluations, edges) of the graph NMS behind a `detect_batch` result, summed over the
+    """(pair tests executed, edges) of the graph NMS behind a `detect_batch` result, summed over the
     batch; None for the bitmask algorithm.  Synchronises.  For bench.py / tests."""
     ws = det.get("nms_ws")
     if ws is None or det.get("algo", NMS_GRAPH) != NMS_GRAPH:
