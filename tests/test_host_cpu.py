@@ -83,6 +83,23 @@ def test_bad_arguments_are_reported(yb):
     assert rc != 0
 
 
+def test_new_entry_points_validate_arguments(yb):
+    """yb_loss_partials_sparse / yb_eval_counts / layout field: bad arguments come back as error codes
+    with a message, before anything touches the GPU."""
+    lib = yb._lib.lib()
+    d = yb._lib.LossDesc()
+    d.S, d.B, d.B_global, d.A, d.nc = 3, 2, 2, 3, 1
+    for s, g in enumerate((8, 4, 2)):
+        d.H[s] = d.W[s] = g
+    assert lib.yb_loss_sparse_workspace_bytes(ctypes.byref(d), 10) > lib.yb_loss_workspace_bytes(ctypes.byref(d))
+    assert lib.yb_loss_partials_sparse(ctypes.byref(d), None, None, None, None, 10, 64, None, None, None, 0, None) != 0
+    d.layout = 7
+    assert lib.yb_loss_partials(ctypes.byref(d), None, None, 0, None) != 0 and b"layout" in lib.yb_last_error()
+    h = yb._lib.HeadsDesc()
+    h.S, h.B, h.A, h.nc, h.layout = 3, 1, 3, 1, 1
+    assert lib.yb_eval_counts(ctypes.byref(h), None, 0.5, 0.5, None, None) != 0
+
+
 def fake_train_module():
     """A stand-in with the reference's hot-path names; internal callers resolve them through the
     module globals exactly like train.py does."""
