@@ -290,14 +290,17 @@ struct RowRec {  // 32 bytes: one address computation serves the box, its area a
     float area;
     u32 rank, cls, pad;
 };
+constexpr int kQueue = kTile + 8;  // sub-tiles queued per level-2 step (<= 32) + < 4 left over
 struct EdgeWarp {
-    RowRec row[kTile];      // rows of tile I
+    RowRec row[kTile + 1];  // rows of tile I; row[kTile] is a sentinel that overlaps nothing (pads the item list)
     float4 col[kTile];      // columns of the current chunk: 4 surviving sub-tiles x 8 boxes
     float carea[kTile];
     RowAux caux[kTile];     // score rank and class of the chunk's columns
     u32 tl[kTile];          // compaction scratch: surviving tiles of the current step
-    u32 sub[kTile * kSubs + 8];  // queue of surviving sub-tile ids (J*kSubs+s); < 4 left over between steps
-    unsigned char item[kTile * kSubs];  // (sub-tile slot << 5) | row, packed work list of a chunk
+    u32 sub[kQueue];        // queue of surviving sub-tile ids (J*kSubs+s) ...
+    float4 sbx[kQueue];     // ... with their bounding boxes ...
+    float2 sar[kQueue];     // ... and area ranges (kept from the level-2 test: no second global read)
+    unsigned short item[kTile * kSubs + kSubs];  // (slot << 11) | (row * 32): packed work list of a chunk
     uint2 ebuf[2 * kTile];  // edges found, flushed to the image's list 33..64 at a time (one atomic per flush)
 };
 
@@ -323,7 +326,7 @@ __device__ __forceinline__ void edge_flush(const GArgs& a, EdgeWarp& w, int b, u
 // evaluates 4 items x 8 columns: all 32 lanes busy whatever the culling pattern.
 __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I, int head,
                                            const float4* __restrict__ sb, const u32* __restrict__ srank,
-                                           const u32* __restrict__ scls, const float4* __restrict__ ss,
+                                           const u32* __restrict__ scls,
                                            uint2* __restrict__ edges, const float4 rq, const bool rvalid,
                                            const float rw_t, const float rh_t, const float rS, const float rS_t,
                                            u32& n_evals, int& n_buf) {
@@ -361,7 +364,8 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
         bool rok = rvalid && e != kNoSub;
         if (rok) {
             if (prune) {
-                const float4 sbx = ss[e * 2], sar = ss[e * 2 + 1];
+                const float4 sbx = w.sbx[head + s];
+                const float2 sar = w.sar[head + s];
                 const float ox = fminf(rq.z, sbx.z) - fmaxf(rq.x, sbx.x);
                 const float oy = fminf(rq.w, sbx.w) - fmaxf(rq.y, sbx.y);
                 rok = ox > 0.0f && oy > 0.0f && ox >= rw_t && oy >= rh_t && sar.y >= rS_t && rS >= t2 * sar.x;
@@ -370,39 +374,44 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, rok);
-        if (rok) w.item[n_items + __popc(m & lt_mask)] = (unsigned char)((s << 5) | lane);
+        if (rok) w.item[n_items + __popc(m & lt_mask)] = (unsigned short)((s << 11) | (lane << 5));
         n_items += __popc(m);
     }
+    if (lane < kSubs) w.item[n_items + lane] = (unsigned short)(kTile << 5);  // pad with the sentinel row
     n_evals += (u32)n_items;
     __syncwarp();
 
+    const float thr = a.thr;
+    const float4* colp = w.col + (lane & (kSub - 1));
+    const float* careap = w.carea + (lane & (kSub - 1));
     for (int it = 0; it < n_items; it += kSubs) {
-        const int idx = it + grp;
-        const bool act = idx < n_items;
-        const u32 item = w.item[act ? idx : it];
-        const int i = item & 31u, slot = item >> 5;
-        const int c = slot * kSub + (lane & (kSub - 1));
-        const RowRec* rr = &w.row[i];
+        const u32 item = w.item[it + grp];
+        const int slot = item >> 11;
+        const int c = slot * kSub;
+        const RowRec* rr = reinterpret_cast<const RowRec*>(reinterpret_cast<const char*>(w.row) + (item & 0x7e0u));
         const float4 r = rr->box;
         const float rarea = rr->area;
-        const float4 q = w.col[c];
-        const float qarea = w.carea[c];
+        const float4 q = colp[c];
+        const float qarea = careap[c];
         const float left = fmaxf(r.x, q.x), right = fminf(r.z, q.z);
         const float top = fmaxf(r.y, q.y), bottom = fminf(r.w, q.w);
         const float iw = fmaxf(right - left, 0.0f), ih = fmaxf(bottom - top, 0.0f);
         const float inter = iw * ih;
         // den within a few ulp of torchvision's fma form whichever box plays `a`: inside the margin
+        // (the sentinel row has zero area and no overlap: d = -tt, never positive)
         const float den0 = (qarea + rarea) - inter;
-        const float tt = a.thr * den0;
+        const float tt = thr * den0;
         const float d = inter - tt;
-        bool pr = act && d > 0.0f;
-        const bool amb = act && (all_exact || !(fabsf(d) > __fmaf_rn(tt, kEps, kTiny)));
+        bool pr = d > 0.0f;
+        const bool amb = all_exact || !(fabsf(d) > __fmaf_rn(tt, kEps, kTiny));
         if (!__any_sync(0xffffffffu, pr || amb)) continue;
         // rare: a candidate edge.  Exact arithmetic where needed, validity, same class, each pair once.
+        const bool act = it + grp < n_items;  // padding items (sentinel row) never make an edge
+        const int i = (int)((item >> 5) & 63u);
         const RowAux ra = {rr->rank, rr->cls};
         const int qp = (int)(sub[slot] * kSub) + (lane & (kSub - 1));
         const bool qvalid = act && qp < M;
-        const RowAux ca = w.caux[c];
+        const RowAux ca = w.caux[c + (lane & (kSub - 1))];
         const u32 crank = ca.rank, ccls = ca.cls;
         if (amb) {
             // torchvision devIoU with a = the higher-scored box
@@ -411,7 +420,7 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
             const float sa = row_a ? rarea : qarea;
             const float bw = row_a ? qw : (r.z - r.x), bh = row_a ? qh : (r.w - r.y);
             const float den = __fmaf_rn(bw, bh, sa) - inter;
-            pr = (inter / den) > a.thr;
+            pr = (inter / den) > thr;
         }
         const bool fin = pr && qvalid && (!class_mode || ccls == ra.cls) && qp > I * kTile + i;
         const unsigned em = __ballot_sync(0xffffffffu, fin);
@@ -463,6 +472,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         const float rw_t = t2 * rw, rh_t = t2 * rh, rS_t = t2 * rS;
         __syncwarp();
         w.row[lane] = RowRec{rq, rS, rrank, rcls, 0u};
+        if (lane == 0) w.row[kTile] = RowRec{make_float4(-far, -far, -far, -far), 0.0f, 0xffffffffu, 0u, 0u};
         __syncwarp();
         const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
         const u32 icmin = __float_as_uint(ia.z), icmax = __float_as_uint(ia.w);
@@ -472,6 +482,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
 
         for (int J0 = I;; J0 += 32) {
             const bool tail = J0 >= info.n_tiles;  // one extra round flushes the last partial chunk
+            int n_t = 0;
             if (tail) {
                 if (n_q == 0) break;
                 if (lane >= n_q && lane < kSubs) w.sub[lane] = kNoSub;
@@ -500,41 +511,53 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                 if (cand == 0u) continue;
                 if (ok) w.tl[__popc(cand & lt_mask)] = (u32)Jl;
                 __syncwarp();
-                const int n_t = __popc(cand);
-                // level 2: lane <-> (surviving tile, sub-tile), 8 tiles per step
-                for (int t0 = 0; t0 < n_t; t0 += 32 / kSubs) {
+                n_t = __popc(cand);
+            }
+            int t0 = 0;
+            do {
+                if (t0 < n_t) {
+                    // level 2: lane <-> (surviving tile, sub-tile), 8 tiles per step
                     const int k = t0 + lane / kSubs;
                     bool sok = k < n_t;
                     u32 e = 0u;
+                    float4 sbx = make_float4(0.f, 0.f, 0.f, 0.f), sar = sbx;
                     if (sok) {
                         e = w.tl[k] * kSubs + (u32)(lane & (kSubs - 1));
                         sok = (int)(e * kSub) < M;
                         if (sok && prune) {
-                            const float4 sbx = ss[e * 2], sar = ss[e * 2 + 1];
+                            sbx = ss[e * 2]; sar = ss[e * 2 + 1];
                             sok = fminf(ib.z, sbx.z) > fmaxf(ib.x, sbx.x) && fminf(ib.w, sbx.w) > fmaxf(ib.y, sbx.y) &&
                                   ia.y >= t2 * sar.x && sar.y >= t2 * ia.x;
                         }
                     }
                     const unsigned sm = __ballot_sync(0xffffffffu, sok);
-                    if (sok) w.sub[n_q + __popc(sm & lt_mask)] = e;
+                    if (sok) {
+                        const int qi = n_q + __popc(sm & lt_mask);
+                        w.sub[qi] = e;
+                        w.sbx[qi] = sbx;
+                        w.sar[qi] = make_float2(sar.x, sar.y);
+                    }
                     n_q += __popc(sm);
+                    __syncwarp();
                 }
-                __syncwarp();
-            }
-            // level 3: chunks of 4 sub-tiles
-            int head = 0;
-            for (; n_q - head >= kSubs; head += kSubs)
-                edge_chunk(a, w, info, b, I, head, sb, srank, scls, ss, edges, rq, rvalid, rw_t, rh_t, rS, rS_t, n_evals,
-                           n_buf);
-            if (head) {  // move the < 4 leftovers to the front
-                const int rem = n_q - head;
-                u32 v = 0u;
-                if (lane < rem) v = w.sub[head + lane];
-                __syncwarp();
-                if (lane < rem) w.sub[lane] = v;
-                __syncwarp();
-                n_q = rem;
-            }
+                // level 3: chunks of 4 sub-tiles
+                int head = 0;
+                for (; n_q - head >= kSubs; head += kSubs)
+                    edge_chunk(a, w, info, b, I, head, sb, srank, scls, edges, rq, rvalid, rw_t, rh_t, rS, rS_t, n_evals,
+                               n_buf);
+                if (head) {  // move the < 4 leftovers to the front
+                    const int rem = n_q - head;
+                    u32 v = 0u;
+                    float4 vb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float2 va = make_float2(0.f, 0.f);
+                    if (lane < rem) { v = w.sub[head + lane]; vb = w.sbx[head + lane]; va = w.sar[head + lane]; }
+                    __syncwarp();
+                    if (lane < rem) { w.sub[lane] = v; w.sbx[lane] = vb; w.sar[lane] = va; }
+                    __syncwarp();
+                    n_q = rem;
+                }
+                t0 += 32 / kSubs;
+            } while (t0 < n_t);
         }
         edge_flush(a, w, b, edges, n_buf);
         if (lane == 0 && n_evals) atomicAdd(&a.info[b].n_evals, (unsigned long long)n_evals);
