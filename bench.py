@@ -274,8 +274,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     T_est = sum(B * G * G * 3 for G in (img // 8, img // 16, img // 32)) * (5 + nc) * 4
     n_sets = 4 if T_est * 3 * 4 <= (8 << 30) else 2
     grids = [img // 8, img // 16, img // 32]
-    from oracle.ref_path import default_anchors  # constants only (train.py:372-374)
-    anchors = [a.to(dev) for a in default_anchors()]
+    anchors = ops.default_anchors(dev)  # train.py:372-374
     weights = ops.MULTISCALE_OBJ_WEIGHTS
 
     # n_sets input sets per rank, on the device and (full run) mirrored in pinned host memory

@@ -20,8 +20,7 @@ sys.path.insert(0, ROOT)
 import yolo_from_scratch_b200 as yb  # noqa: E402
 from yolo_from_scratch_b200 import ops  # noqa: E402
 
-ANCH = [torch.tensor(a, dtype=torch.float32) for a in (
-    [[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]], [[116, 90], [156, 198], [373, 326]])]
+ANCH = ops.default_anchors()
 
 
 def main():

@@ -33,6 +33,11 @@ CLS_WEIGHT = 0.5                  # train.py:836
 MULTISCALE_OBJ_WEIGHTS = (4.0, 1.0, 0.4)  # train.py:865
 LOSS_DECODE_IMG_SIZE = 640.0      # train.py:796 — yolo_loss always decodes with the default
 CIOU_EPS = 1e-7                   # train.py:634
+DEFAULT_ANCHORS = (               # train.py:372-374 (model) / :81-83 (dataset): P3, P4, P5 anchors in pixels
+    ((10, 13), (16, 30), (33, 23)),
+    ((30, 61), (62, 45), (59, 119)),
+    ((116, 90), (156, 198), (373, 326)),
+)
 TRICK_MAX_NUMEL_CUDA = 100_000    # torchvision/ops/boxes.py:80
 TRICK_MAX_NUMEL_CPU = 4_000
 
@@ -92,6 +97,11 @@ def _anchors_dev(anchors, dev: torch.device) -> torch.Tensor:
         _anchor_cache[key] = (host.clone(), out)
         return out
     return torch.tensor(anchors, dtype=torch.float32, device=dev).reshape(-1, 2).contiguous()
+
+
+def default_anchors(device=None) -> List[torch.Tensor]:
+    """The reference's default anchors as three (3,2) fp32 tensors (train.py:372-374)."""
+    return [torch.tensor(a, dtype=torch.float32, device=device) for a in DEFAULT_ANCHORS]
 
 
 def _check_head(t: torch.Tensor, what: str):
