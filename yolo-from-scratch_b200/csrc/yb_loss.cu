@@ -177,6 +177,8 @@ struct LossArgs {
     LossScale sc[YB_MAX_SCALES];
     int* pos_count;      // [YB_MAX_SCALES] in ws
     uint32_t* pos_list;  // ws
+    int fuse_norm;               // single rank (B_global == B): the positive kernel writes final gradients
+    float coef_box[YB_MAX_SCALES], coef_cls[YB_MAX_SCALES];
     const uint32_t* pos_ent;     // sparse targets: entry id of each listed row
     const SparseEntry* entries;  // sparse targets: target rows
     double* partials;    // S*4: {sum(1-ciou), n_pos, sum bce_obj, sum bce_cls}
@@ -384,6 +386,13 @@ __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
         const LossScale& L = a.sc[s];
         const uint32_t P = (uint32_t)a.pos_count[s];
         double acc_box = 0.0, acc_cls = 0.0;
+        // single rank: the local positive count IS the global one, so the normalisation that
+        // loss_finalize_kernel would apply (same two roundings: unnormalised value, then * k) happens here
+        float k_box = 1.0f, k_cls = 1.0f;
+        if (a.fuse_norm && P > 0) {
+            k_box = (float)((double)a.coef_box[s] / (double)P);
+            k_cls = a.nc > 0 ? (float)((double)a.coef_cls[s] / ((double)P * (double)a.nc)) : 0.0f;
+        }
         for (uint32_t k = gwarp; k < P; k += nwarps) {
             const uint32_t r = a.pos_list[L.list_begin + k];
             uint32_t cs;
@@ -410,7 +419,10 @@ __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
                 const float xc = x[(size_t)(5 + c) * cs];
                 const float tc = SPARSE ? (c == ent.cls ? 1.0f : 0.0f) : t[5 + c];
                 cls += bce_logits_ref(xc, tc);
-                if (L.grad) L.grad[xb + (size_t)(5 + c) * cs] = sigmoidf_ref(xc) - tc;
+                if (L.grad) {
+                    const float g = sigmoidf_ref(xc) - tc;
+                    L.grad[xb + (size_t)(5 + c) * cs] = a.fuse_norm ? g * k_cls : g;
+                }
             }
             cls = warp_sum(cls);
             if (L.grad && lane < 4) {
@@ -425,7 +437,7 @@ __global__ void __launch_bounds__(256) loss_positive_kernel(const LossArgs a) {
                     const float u = 2.0f * sgm;
                     g = (((gp[lane] * (anc * a.inv_img)) * (2.0f * u)) * 2.0f) * ds;
                 }
-                L.grad[xb + (size_t)lane * cs] = g;
+                L.grad[xb + (size_t)lane * cs] = a.fuse_norm ? g * k_box : g;
             }
             acc_box += (double)l;
             acc_cls += (double)cls;
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const FinalizeArgs f
     const uint32_t nwarps = gridDim.x * warps_per_cta;
     for (int s = 0; s < a.S; ++s) {
         const LossScale& L = a.sc[s];
-        if (!L.grad) continue;
+        if (!L.grad || a.fuse_norm) continue;         // fused: loss_positive_kernel already normalised
         const uint32_t P = (uint32_t)a.pos_count[s];  // local positives
         const double Pg = f.partials[s * 4 + 1];      // global positives
         if (P == 0 || Pg <= 0.0) continue;
@@ -559,6 +571,8 @@ static void loss_fill_args(const yb_loss_desc* d, void* ws, LossArgs& a) {
     a.n_tiles = tile;
     a.pos_ent = nullptr;
     a.entries = nullptr;
+    a.fuse_norm = d->B_global == (long long)d->B ? 1 : 0;
+    for (int s = 0; s < d->S; ++s) { a.coef_box[s] = d->coef_box[s]; a.coef_cls[s] = d->coef_cls[s]; }
 }
 
 // sparse-target workspace: [dense-layout workspace][pos_ent: rows u32][entries][bits]
@@ -720,7 +734,7 @@ extern "C" int yb_loss_finalize(const yb_loss_desc* d, const double* partials, f
         f.coef_cls[s] = d->coef_cls[s];
         any_grad |= d->grad[s] != nullptr;
     }
-    const int blocks = (any_grad && f.a.n_tiles > 0) ? sm_count() : 1;
+    const int blocks = (any_grad && f.a.n_tiles > 0 && !f.a.fuse_norm) ? sm_count() : 1;
     cudaStream_t st = (cudaStream_t)stream;
     YB_LAUNCH("loss_finalize_kernel", st, loss_finalize_kernel<<<blocks, 256, 0, st>>>(f));
     return 0;

@@ -617,7 +617,9 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
         if (!__syncthreads_or(left)) break;
     }
     // ---- emit kept indices in descending score order (K is indexed by score rank) ----
-    const u32* order = a.order + (size_t)b * a.cap;
+    // word prefix sums (fK reused), then one thread per rank: coalesced reads of `order`, near-coalesced writes
+    const u32* __restrict__ order = a.order + (size_t)b * a.cap;
+    int64_t* __restrict__ keep = a.keep + (size_t)b * a.cap;
     const int chunk = (nw + kResolveThreads - 1) / kResolveThreads;
     const int c0 = min(tid * chunk, nw), c1 = min(c0 + chunk, nw);
     u32 sum = 0;
@@ -635,14 +637,14 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
         if (w < warp) base += s_scan[w];
         total += s_scan[w];
     }
-    int64_t* keep = a.keep + (size_t)b * a.cap;
     for (int w = c0; w < c1; ++w) {
-        u32 bits = K[w];
-        while (bits) {
-            const int j = __ffs(bits) - 1;
-            bits &= bits - 1u;
-            keep[base++] = (int64_t)order[w * 32 + j];
-        }
+        fK[w] = base;
+        base += __popc(K[w]);
+    }
+    __syncthreads();
+    for (int r = tid; r < M; r += kResolveThreads) {
+        const u32 bits = K[r >> 5];
+        if ((bits >> (r & 31)) & 1u) keep[fK[r >> 5] + __popc(bits & ((1u << (r & 31)) - 1u))] = (int64_t)order[r];
     }
     if (tid == 0) a.n_keep[b] = (int)total;
 }
