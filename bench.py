@@ -51,6 +51,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
+                    help="what `value` times: the step replayed as a CUDA graph (yb.HotPathGraph; at N>1 the NCCL "
+                         "all-reduce is captured inside the graph), or eager launches.  Per-kernel times always come "
+                         "from an eager pass; both throughputs are reported.")
+    ap.add_argument("--graph-multi-gpu", action="store_true", help=argparse.SUPPRESS)  # kept for old command lines
     ap.add_argument("--layout", default="bhwac", choices=["bhwac", "nchw"],
                     help="head layout of the device-resident step: the reference's (B,H,W,A,5+nc) or the head conv's own "
                          "NCHW output (SURVEY 8f-2)")
@@ -391,9 +396,10 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
 
     # ---- the same device-resident step replayed as CUDA graphs (one graph per rotating input set) ----
     graph_ms = graph_err = None
-    if full and world == 1:
+    if full and args.launch == "graph":
         try:
-            graph_ms = time_graph_replay(args, yb, dev_sets, anchors, layout, use_labels, n_sets)
+            graph_ms = time_graph_replay(args, yb, dev_sets, anchors, layout, use_labels, n_sets, group, barrier,
+                                         max_over_ranks)
         except Exception as e:  # pragma: no cover  (an optional leg must not lose the whole line)
             graph_err = repr(e)
 
@@ -522,15 +528,22 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         except Exception as e:  # pragma: no cover
             torch_gpu = {"error": repr(e)}
 
+    eager = {"value": B * world / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "unit": UNIT,
+             "what": "the same K steps with eager launches (one launch per kernel from Python/ctypes)"}
+    use_graph = graph_ms is not None
+    step_ms = graph_ms if use_graph else ms_per_step
     line = {
-        "metric": METRIC, "value": B * world / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "metric": METRIC, "value": B * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "launch": ("cuda-graph replay (yb.HotPathGraph, one graph per rotating input set" +
+                   (", NCCL all-reduce captured inside" if world > 1 else "") + ")") if use_graph else "eager",
+        "eager": eager,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world, n_sets),
         "graph_replay": ({"error": graph_err} if graph_err else None) if graph_ms is None else {
             "ms_per_step": graph_ms, "value": B * world / (graph_ms * 1e-3), "unit": UNIT,
-            "what": "the same device-resident step (plus detection packing) replayed as one CUDA graph per input set "
-                    "(yb.HotPathGraph): launch gaps removed"},
+            "what": "the device-resident step (loss fwd+bwd, decode+filter+NMS, plus detection packing) replayed as one "
+                    "CUDA graph per input set: launch gaps removed"},
         "loss_fwd_bwd_ms": loss_ms, "decode_nms_ms": det_ms, "decode_nms_images_per_s": B * world / (det_ms * 1e-3),
         "candidates_per_image": float(np.mean(cand_counts)) / B, "kept_per_image": float(np.mean(keep_counts)) / B,
         "e2e": e2e, "e2e_labels": e2e_labels, "e2e_graph": e2e_graph, "gpu_launches": int(launches), "kernels": kernels,
@@ -541,20 +554,22 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     return line
 
 
-def time_graph_replay(args, yb, dev_sets, anchors, layout, use_labels, n_sets):
-    """ms per device-resident step when the step is replayed as CUDA graphs, one per rotating input set."""
+def time_graph_replay(args, yb, dev_sets, anchors, layout, use_labels, n_sets, group, barrier, max_over_ranks):
+    """ms per device-resident step when the step is replayed as CUDA graphs, one per rotating input set
+    (max over ranks; with a process group the loss all-reduce is captured inside the graphs)."""
     graphs = [yb.HotPathGraph(args.batch, args.img, args.nc, anchors, args.conf, args.iou, max_gt=MAX_GT, layout=layout,
-                              adopt_heads=ds[0], adopt_targets=ds[2] if use_labels else ds[1]) for ds in dev_sets]
+                              adopt_heads=ds[0], adopt_targets=ds[2] if use_labels else ds[1], group=group)
+              for ds in dev_sets]
     for i in range(max(3, args.warmup)):
         graphs[i % n_sets].replay()
-    torch.cuda.synchronize()
+    barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for i in range(args.steps):
         graphs[i % n_sets].replay()
     g1.record()
-    torch.cuda.synchronize()
-    ms = g0.elapsed_time(g1) / args.steps
+    barrier()
+    ms = max_over_ranks(g0.elapsed_time(g1)) / args.steps
     assert int(graphs[0].det["n_keep"].min()) >= 0
     del graphs
     torch.cuda.empty_cache()

@@ -5,7 +5,8 @@ import sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 def kern(o):
     return {k: (round(v['avg_ms'] * 1e3, 1), round(v['share'], 3)) for k, v in o['kernels'].items()}
-print({k: d.get(k) for k in ['value', 'ms_per_step', 'loss_fwd_bwd_ms', 'decode_nms_ms', 'n_gpus']})
+print({k: d.get(k) for k in ['value', 'ms_per_step', 'launch', 'loss_fwd_bwd_ms', 'decode_nms_ms', 'n_gpus']})
+print('eager', d.get('eager'))
 print('e2e', d.get('e2e'))
 for k in ('e2e_labels', 'e2e_graph', 'graph_replay'):
     if d.get(k):

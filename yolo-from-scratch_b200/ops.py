@@ -800,9 +800,11 @@ class HotPathGraph:
 
     def __init__(self, batch, img_size, num_classes, anchors_list, conf_threshold=0.5, iou_threshold=0.4, max_gt=50,
                  targets="labels", layout=LAYOUT_BHWAC, num_anchors=3, device=None, adopt_heads=None,
-                 adopt_targets=None):
+                 adopt_targets=None, group=None):
         """adopt_heads / adopt_targets: existing device tensors (or a PackedLabels) to use as the static
-        inputs instead of allocating new ones."""
+        inputs instead of allocating new ones.  group: torch.distributed process group of an image-sharded
+        job; the all-reduce of the loss partials is then captured inside the graph (NCCL)."""
+        self.group = group
         dev = _device() if device is None else torch.device(device)
         self.device, self.nc, self.img, self.layout = dev, int(num_classes), int(img_size), layout
         row = 5 + self.nc
@@ -845,7 +847,8 @@ class HotPathGraph:
 
     def _step(self):
         out4, _, grads = loss_forward_backward(self.heads, self.targets, self.anchors, self.nc, MULTISCALE_OBJ_WEIGHTS,
-                                               [True] * len(self.heads), sparse=self.labels, layout=self.layout)
+                                               [True] * len(self.heads), sparse=self.labels, layout=self.layout,
+                                               group=self.group)
         det = detect_batch(self.heads, self.anchors, self.img, self.nc, self.conf, self.iou, layout=self.layout)
         rows, offsets = pack_detections(det)
         return out4, grads, det, rows, offsets
