@@ -546,7 +546,10 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
                     "CUDA graph per input set: launch gaps removed"},
         "loss_fwd_bwd_ms": loss_ms, "decode_nms_ms": det_ms, "decode_nms_images_per_s": B * world / (det_ms * 1e-3),
         "candidates_per_image": float(np.mean(cand_counts)) / B, "kept_per_image": float(np.mean(keep_counts)) / B,
-        "e2e": e2e, "e2e_labels": e2e_labels, "e2e_graph": e2e_graph, "gpu_launches": int(launches), "kernels": kernels,
+        "e2e": e2e, "e2e_labels": e2e_labels, "e2e_graph": e2e_graph, "gpu_launches": int(launches),
+        "gpu_launches_note": "kernels of libyolo_b200.so enqueued during the K eager steps (the per-kernel table); a graph "
+                             "replay runs the same kernels plus pack_kernel from one cudaGraphLaunch",
+        "kernels": kernels,
         "roofline": roofline, "hbm_kernels": hbm_kernels, "roofline_nms": nms_roof, "cpu_baseline": cpu_baseline,
         "torch_gpu_baseline": torch_gpu, "clocks": clocks, "variants": variants,
     }
