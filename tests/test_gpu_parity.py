@@ -593,7 +593,8 @@ def test_nms_ties_degenerate_and_nan(yb, algo):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("n,nc,neg", [(800, 4, 0.0), (800, 4, 200.0), (24000, 80, 100.0), (26000, 80, 100.0), (26000, 1, 0.0)])
+@pytest.mark.parametrize("n,nc,neg", [(800, 4, 0.0), (800, 4, 200.0), (24000, 80, 100.0), (26000, 80, 100.0), (26000, 1, 0.0),
+                                      (30000, 3, 50.0)])  # 30000 > 26,880: the graph NMS sorts with the ballot kernel
 def test_batched_nms_both_regimes(yb, n, nc, neg, algo):
     """n <= 25000 uses torchvision's coordinate trick (incl. its negative-coordinate cross-class
     quirk), larger n its per-class loop (boxes.py:80)."""
