@@ -800,11 +800,14 @@ class HotPathGraph:
 
     def __init__(self, batch, img_size, num_classes, anchors_list, conf_threshold=0.5, iou_threshold=0.4, max_gt=50,
                  targets="labels", layout=LAYOUT_BHWAC, num_anchors=3, device=None, adopt_heads=None,
-                 adopt_targets=None, group=None):
+                 adopt_targets=None, group=None, overlap_loss=True):
         """adopt_heads / adopt_targets: existing device tensors (or a PackedLabels) to use as the static
         inputs instead of allocating new ones.  group: torch.distributed process group of an image-sharded
-        job; the all-reduce of the loss partials is then captured inside the graph (NCCL)."""
+        job; the all-reduce of the loss partials is then captured inside the graph (NCCL).
+        overlap_loss: the loss kernels (HBM-bound, few resident warps) and the filter/NMS kernels (issue-bound)
+        are independent readers of the heads; they are captured as two parallel branches of the graph."""
         self.group = group
+        self.overlap_loss = bool(overlap_loss)
         dev = _device() if device is None else torch.device(device)
         self.device, self.nc, self.img, self.layout = dev, int(num_classes), int(img_size), layout
         row = 5 + self.nc
@@ -834,6 +837,7 @@ class HotPathGraph:
             else:
                 raise ValueError("targets must be 'labels' or 'dense'")
             self.conf, self.iou = float(conf_threshold), float(iou_threshold)
+            self._branch = torch.cuda.Stream(device=dev) if self.overlap_loss else None
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -845,12 +849,24 @@ class HotPathGraph:
             with torch.cuda.graph(self.graph):
                 self.losses, self.grads, self.det, self.rows, self.offsets = self._step()
 
-    def _step(self):
+    def _loss(self):
         out4, _, grads = loss_forward_backward(self.heads, self.targets, self.anchors, self.nc, MULTISCALE_OBJ_WEIGHTS,
                                                [True] * len(self.heads), sparse=self.labels, layout=self.layout,
                                                group=self.group)
+        return out4, grads
+
+    def _step(self):
+        cur = torch.cuda.current_stream()
+        if self._branch is not None:      # fork: loss on a second stream, joined before the step ends
+            self._branch.wait_stream(cur)
+            with torch.cuda.stream(self._branch):
+                out4, grads = self._loss()
+        else:
+            out4, grads = self._loss()
         det = detect_batch(self.heads, self.anchors, self.img, self.nc, self.conf, self.iou, layout=self.layout)
         rows, offsets = pack_detections(det)
+        if self._branch is not None:
+            cur.wait_stream(self._branch)
         return out4, grads, det, rows, offsets
 
     def replay(self):
