@@ -13,14 +13,19 @@ once per step over NCCL, NMS needs no collective.
 
 `value` is timed with the inputs resident in HBM; `e2e` goes through the public Python API with
 pinned HOST buffers (H2D of heads+targets and D2H of losses + detections inside the timed region).
-`--impl reference` times the oracle port of the reference's CPU implementation (torch CPU ops +
-torchvision's CPU nms, the code path train.py runs on a host without CUDA) on a bounded sample.
-One JSON line is printed by rank 0.
+`--impl reference` times the reference's CPU implementation of the path on the host cores: the
+UNMODIFIED reference (baseline/_ref/train.py: yolo_loss_multiscale + predict) when it has been staged,
+else the oracle port of the same code path.
+
+Rank 0 prints ONE compact JSON line (< 4 KB: the contract keys + roofline + hbm_kernels + cpu_baseline +
+e2e).  The per-kernel tables, the other BASELINE configs and every variant go to
+profiles/bench_last_full.json (--full-out).
 """
 import argparse
 import ctypes
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -35,12 +40,14 @@ IMG, NC, B_PER_GPU, MAX_GT = 640, 1, 64, 50
 CONF, IOU = 0.5, 0.4
 METRIC = "decode+global-NMS + CIoU-loss fwd+bwd throughput @640^2 bs64 nc1"
 UNIT = "images/s"
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+MAX_LINE_BYTES = 4096
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nc", type=int, default=NC)
@@ -48,21 +55,33 @@ def parse():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU")
     ap.add_argument("--conf", type=float, default=CONF)
     ap.add_argument("--iou", type=float, default=IOU)
+    ap.add_argument("--reps", type=int, default=7,
+                    help="the K-step timed region is repeated this many times, each bracketed by barrier + sync; "
+                         "ms_per_step is the median over the repetitions and the spread is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
                     help="what `value` times: the step replayed as a CUDA graph (yb.HotPathGraph; at N>1 the NCCL "
                          "all-reduce is captured inside the graph), or eager launches.  Per-kernel times always come "
-                         "from an eager pass; both throughputs are reported.")
-    ap.add_argument("--graph-multi-gpu", action="store_true", help=argparse.SUPPRESS)  # kept for old command lines
+                         "from an eager pass of the same K steps; both throughputs are reported.")
     ap.add_argument("--layout", default="bhwac", choices=["bhwac", "nchw"],
                     help="head layout of the device-resident step: the reference's (B,H,W,A,5+nc) or the head conv's own "
                          "NCHW output (SURVEY 8f-2)")
     ap.add_argument("--targets", default="dense", choices=["dense", "labels"],
                     help="dense reference targets, or label lists assigned on the device (SURVEY 8f-4)")
     ap.add_argument("--no-torch-gpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--numa", default="auto", choices=["auto", "off"],
+                    help="auto: bind the rank to its GPU's local CPUs (nvml) before the pinned host buffers are allocated")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="images per step of the reference arm / cpu_baseline leg: N > 0 = exactly N, -1 = every image of the "
+                         "batch, 0 = auto: as many (same seeds, first images of the batch) as keep the whole K+W-step run "
+                         "within --cpu-budget-s, measured on a 2-image calibration pass")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--full-out", default=os.path.join(ROOT, "profiles", "bench_last_full.json"),
+                    help="file that receives the full, uncompacted result ('' = none)")
+    return ap.parse_args(argv)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -91,6 +110,17 @@ def make_heads(B, img, nc, seed):
 
 def tensor_bytes(ts):
     return int(sum(t.numel() * t.element_size() for t in ts))
+
+
+def r3(x):
+    """3 significant digits for the compact line."""
+    if x is None:
+        return None
+    x = float(x)
+    if x == 0.0 or x != x:
+        return x
+    from math import floor, log10
+    return round(x, max(0, 2 - int(floor(log10(abs(x))))))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -133,7 +163,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.003)
 
     def summary(self):
         if not self.ok or not self.samples:
@@ -142,90 +172,200 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: oracle port of the reference's CPU path
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_step(heads, tgts, anchors, nc, img, conf, iou, pool, use_tv):
-    """loss fwd+bwd (torch CPU, all threads) + per-image decode/filter/NMS (train.py:1152-1238)."""
-    from oracle import ref_path as R
-    preds = [h.clone().requires_grad_(True) for h in heads]
-    total = R.multiscale_loss(preds, tgts, anchors, nc)[0]
-    total.backward()
-    B = heads[0].shape[0]
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs nvml reports as local to GPU `index`, so that the pinned host buffers
+    allocated afterwards are first-touched on that NUMA node (the H2D path then does not cross the
+    socket interconnect).  Returns a short description for the result line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and w * 64 + b < n_cpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "off (nvml reports no local CPUs)"
+        os.sched_setaffinity(0, allowed)
+        return f"gpu-local cpus ({len(allowed)} of {n_cpu})"
+    except Exception as e:  # pragma: no cover
+        return f"off ({type(e).__name__})"
 
-    def one(b):
-        bx, sc, cl = R.candidates([h[b:b + 1] for h in heads], anchors, img, nc, conf)
-        if bx.shape[0] == 0:
-            return 0
-        if use_tv:
-            import torchvision
-            return int(torchvision.ops.batched_nms(bx, sc, cl, iou).numel())
-        return len(R.batched_nms_indices(bx.numpy(), sc.numpy(), cl.numpy(), iou, "cpu", "cpu"))
-    kept = list(pool.map(one, range(B)))
-    return float(total), kept
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's CPU implementation of the path on the host cores
+# ------------------------------------------------------------------------------------------------
+class _PresetHeadsModel:
+    """Stands in for the YOLO model inside the reference's predict(): the conv backbone is out of scope
+    (SURVEY 8), so the model call returns the synthetic heads of the image being predicted."""
+
+    def __init__(self, img_size, anchors):
+        self.img_size, self.anchors, self.heads = img_size, anchors, None
+
+    def eval(self):
+        return self
+
+    def __call__(self, img):
+        return self.heads
+
+
+def load_unmodified_reference():
+    """The reference's train.py as staged (byte-identical copy) in baseline/_ref by __graft_entry__.build();
+    None when it is not there (then the oracle port of the same code path is used)."""
+    path = os.path.join(REF_DIR, "train.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("yolo_reference_train_unmodified", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def run_cpu_reference(args, sample_images, steps, warmup):
+    """loss fwd+bwd (torch CPU, all threads) + per-image decode/filter/NMS (train.py:1152-1238), images spread
+    over the host threads.  Returns (images/s, ms per step, cores, kind, sample description)."""
     from concurrent.futures import ThreadPoolExecutor
-    from oracle import ref_path as R
-    try:
-        import torchvision  # noqa: F401
-        use_tv = True
-    except Exception:
-        use_tv = False
-    cores = os.cpu_count() or 1
+    import tempfile
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
-    anchors = R.default_anchors()
+    ref = load_unmodified_reference()
     heads = [h[:sample_images].contiguous() for h in make_heads(args.batch, args.img, args.nc, 1234)]
     labels = make_labels(np.random.default_rng(4321), args.batch, args.nc)[:sample_images]
     grids = [args.img // 8, args.img // 16, args.img // 32]
+    from oracle import ref_path as R   # the CPU arm is the one place bench.py may execute oracle/
+    anchors = R.default_anchors()
     tg = [R.assign_targets(l, anchors, grids, args.nc, args.img) for l in labels]
     tgts = [torch.from_numpy(np.stack([t[s] for t in tg])) for s in range(3)]
-    pool = ThreadPoolExecutor(max_workers=min(cores, sample_images))
+    workers = max(1, min(cores, sample_images))
+    pool = ThreadPoolExecutor(max_workers=workers)
+    tmp = tempfile.TemporaryDirectory()
+    if ref is not None:
+        from PIL import Image
+        img_path = os.path.join(tmp.name, "blank.png")  # letterbox identity: predict() reads it, the preset heads ignore it
+        Image.fromarray(np.zeros((args.img, args.img, 3), dtype=np.uint8)).save(img_path)
+        cpu = torch.device("cpu")
+
+        def one(b):
+            m = _PresetHeadsModel(args.img, anchors)
+            m.heads = [h[b:b + 1] for h in heads]
+            return len(ref.predict(m, img_path, cpu, num_classes=args.nc, conf_threshold=args.conf, iou_threshold=args.iou))
+
+        def loss():
+            preds = [h.clone().requires_grad_(True) for h in heads]
+            total = ref.yolo_loss_multiscale(preds, tgts, anchors, args.nc)[0]
+            total.backward()
+            return float(total.detach())
+        kind = "reference"
+        what = "UNMODIFIED reference (baseline/_ref/train.py): yolo_loss_multiscale(...).backward() on torch CPU + predict() per image on preset heads (torchvision CPU batched_nms)"
+    else:
+        import torchvision
+
+        def one(b):
+            bx, sc, cl = R.candidates([h[b:b + 1] for h in heads], anchors, args.img, args.nc, args.conf)
+            return int(torchvision.ops.batched_nms(bx, sc, cl, args.iou).numel()) if bx.shape[0] else 0
+
+        def loss():
+            preds = [h.clone().requires_grad_(True) for h in heads]
+            total = R.multiscale_loss(preds, tgts, anchors, args.nc)[0]
+            total.backward()
+            return float(total.detach())
+        kind = "port"
+        what = "oracle port of the reference's CPU path: loss fwd+bwd on torch CPU + per-image decode/filter/torchvision CPU batched_nms"
+
+    def step():
+        loss()
+        return list(pool.map(one, range(sample_images)))
+
     for _ in range(warmup):
-        cpu_reference_step(heads, tgts, anchors, args.nc, args.img, args.conf, args.iou, pool, use_tv)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(heads, tgts, anchors, args.nc, args.img, args.conf, args.iou, pool, use_tv)
-    dt = (time.perf_counter() - t0) / steps
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
     pool.shutdown()
-    sample = (f"{sample_images} of {args.batch} images per step (same seeds), loss fwd+bwd on torch CPU + per-image "
-              f"decode/filter/{'torchvision CPU batched_nms' if use_tv else 'nms_ref.c'}; images spread over {min(cores, sample_images)} threads")
-    return sample_images / dt, dt * 1e3, cores, sample
+    tmp.cleanup()
+    sample = f"{sample_images} of {args.batch} images/step, {steps} steps; {what}; {workers} threads"
+    return sample_images / dt, dt * 1e3, cores, kind, sample
 
 
 def reference_main(args, rank):
     if rank != 0:
         return
-    sample_images = max(1, min(args.batch, 8))
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    v, ms, cores, sample = run_cpu_reference(args, sample_images, steps, warmup)
+    if hasattr(os, "sched_setaffinity"):
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except OSError:
+            pass
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if args.cpu_sample > 0:
+        sample_images = max(1, min(args.batch, args.cpu_sample))
+    elif args.cpu_sample < 0:
+        sample_images = args.batch
+    else:  # bounded sample: a calibration pass on 2 images sizes the step so that K+W steps fit the budget
+        n_cal = min(2, args.batch)
+        _, ms_cal, _, _, _ = run_cpu_reference(args, n_cal, 1, 0)
+        per_image_s = ms_cal * 1e-3 / n_cal
+        sample_images = int(max(1, min(args.batch, args.cpu_budget_s / ((steps + warmup) * per_image_s))))
+    v, ms, cores, kind, sample = run_cpu_reference(args, sample_images, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_subprocess(args):
+    """cpu_baseline of the product line: the reference arm in a fresh process (no CUDA context, full CPU
+    affinity), bounded: 2 steps + 1 warm-up over the batch (about 10-20 s)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--nc", str(args.nc), "--img", str(args.img), "--batch", str(args.batch), "--conf", str(args.conf),
+           "--iou", str(args.iou), "--cpu-sample", str(args.cpu_sample), "--cpu-budget-s", "25"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        d = json.loads(lines[-1])
+        cb = d["cpu_baseline"]
+        cb["ms_per_step"] = d["ms_per_step"]
+        return cb
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e!r}"[:200]}
+
+
 def workload_config(args, world, n_sets=4):
+    base = (args.nc, args.img, args.batch) == (1, 640, 64)
     return {
-        "head_layout": args.layout, "targets": args.targets,
-        "workload": f"BASELINE {'configs[1]' if (args.nc, args.img, args.batch) == (1, 640, 64) else 'variant'}: nc={args.nc} heads at {args.img}x{args.img}, {args.batch} images/GPU, "
-                    f"<= {MAX_GT} GT boxes/image, randn heads, conf {args.conf}, iou {args.iou}",
+        "workload": f"BASELINE {'configs[1]' if base else 'variant'}: nc={args.nc} heads {args.img}x{args.img}, "
+                    f"{args.batch} images/GPU, <={MAX_GT} GT/image, randn heads, conf {args.conf}, iou {args.iou}",
         "global_batch": args.batch * world, "images_per_gpu": args.batch, "img_size": args.img, "nc": args.nc,
         "conf_thres": args.conf, "iou_thres": args.iou, "parallelism": f"image-sharded x{world}",
-        "l2": f"inputs rotate over {n_sets} sets per rank (working set > 126 MB L2)",
+        "head_layout": args.layout, "targets": args.targets,
+        "l2": f"inputs rotate over {n_sets} sets/rank (> 126 MB L2)",
     }
 
 
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+OTHER_CONFIGS = {  # BASELINE.json configs[2], configs[3]: (nc, img, images/GPU, conf, head layout, targets)
+    "cfg2_nc80_640_B64_conf.001": (80, 640, 64, 0.001, "bhwac", "dense"),
+    "cfg3_nc80_1280_B32_conf.001": (80, 1280, 32, 0.001, "bhwac", "dense"),
+    # the same work on the 'next' rows of SURVEY 8f: NCHW conv output read directly + label-list targets
+    "cfg1_nchw_labels": (1, 640, 64, 0.5, "nchw", "labels"),
+    "cfg2_nchw_labels": (80, 640, 64, 0.001, "nchw", "labels"),
+}
+SHARDED_CONFIGS = {  # BASELINE.json configs[4]: nc=80, 640^2, global batch 64 x N sharded by image (N=8: 512)
+    "cfg4_nc80_640_B64perGPU_conf.001": (80, 640, 64, 0.001, "bhwac", "dense"),
+}
+
+
 def b200_main(args, rank, local_rank, world):
     import yolo_from_scratch_b200 as yb
     lib = yb._lib.lib()  # raises if the CUDA extension is missing: no fallback
@@ -233,42 +373,150 @@ def b200_main(args, rank, local_rank, world):
         raise RuntimeError("bench.py (impl b200) needs a GPU; the CUDA path has no fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if args.numa == "auto" else "off"
     group = None
     if world > 1:
         import torch.distributed as dist
         import datetime
         # a short collective timeout: a rank-asymmetric bug must fail in minutes, not hold N GPUs for the default 10
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
         group = dist.group.WORLD
-    line = run_workload(args, rank, local_rank, world, dev, group, lib, full=True)
-    if rank == 0 and not args.no_other_configs and world == 1:
-        # the other single-GPU BASELINE configs, device-resident only, short runs (parity is in tests/)
+    full = run_workload(args, rank, local_rank, world, dev, group, lib, full=True)
+    others = {}
+    if not args.no_other_configs:
         import copy
-        others = {}
-        for name, (nc, img, batch, conf, layout, targets) in OTHER_CONFIGS.items():
+        for name, (nc, img, batch, conf, layout, targets) in (OTHER_CONFIGS if world == 1 else SHARDED_CONFIGS).items():
             a2 = copy.copy(args)
             a2.nc, a2.img, a2.batch, a2.conf, a2.layout, a2.targets = nc, img, batch, conf, layout, targets
-            a2.steps, a2.warmup = max(3, min(args.steps, 6)), 3
-            try:
-                o = run_workload(a2, rank, local_rank, world, dev, group, lib, full=False)
-                others[name] = {k: o[k] for k in ("value", "ms_per_step", "loss_fwd_bwd_ms", "decode_nms_ms",
-                                                  "candidates_per_image", "kept_per_image", "kernels", "hbm_kernels",
-                                                  "roofline", "config")}
-            except Exception as e:  # pragma: no cover
-                others[name] = {"error": repr(e)}
+            a2.steps, a2.warmup, a2.reps = max(3, min(args.steps, 6)), 3, 3
+            o = run_workload(a2, rank, local_rank, world, dev, group, lib, full=False)   # every rank takes part
+            if rank == 0:
+                others[name] = o
             torch.cuda.empty_cache()
-        line["other_configs"] = others
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    dist_parity = None
+    if world > 1:
+        dist_parity = check_dist_parity(yb, dev, rank, world, group)
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+        if not dist_parity["ok"]:
+            raise SystemExit(f"sharded loss differs from the single-rank loss: {dist_parity}")
+    if rank != 0:
+        return
+    full["numa"] = numa
+    full["other_configs"] = others
+    full["dist_parity"] = dist_parity
+    if not args.no_cpu_baseline:
+        full["cpu_baseline"] = cpu_baseline_subprocess(args)
+    line = compact_line(full)
+    if args.full_out:
+        try:
+            os.makedirs(os.path.dirname(args.full_out), exist_ok=True)
+            with open(args.full_out, "w") as f:
+                json.dump(full, f, indent=1)
+        except OSError as e:  # pragma: no cover
+            print(f"bench.py: could not write {args.full_out}: {e}", file=sys.stderr)
+    print(json.dumps(line, separators=(",", ":")), flush=True)
 
 
-OTHER_CONFIGS = {  # BASELINE.json configs[2], configs[3]: (nc, img, images/GPU, conf, head layout, targets)
-    "configs[2] nc80 640^2 B64 conf0.001": (80, 640, 64, 0.001, "bhwac", "dense"),
-    "configs[3] nc80 1280^2 B32 conf0.001": (80, 1280, 32, 0.001, "bhwac", "dense"),
-    # the same work on the 'next' rows of SURVEY 8f: NCHW conv output read directly + label-list targets
-    "configs[1] nc1 640^2 B64 conf0.5, NCHW heads + label lists": (1, 640, 64, 0.5, "nchw", "labels"),
-    "configs[2] nc80 640^2 B64 conf0.001, NCHW heads + label lists": (80, 640, 64, 0.001, "nchw", "labels"),
-}
+def compact_line(full):
+    """The ONE line the driver parses: the contract keys plus roofline, hbm_kernels (name -> [us, frac of the
+    measured HBM peak]), cpu_baseline and e2e; everything else stays in the full result file."""
+    def pick(d, keys):
+        return None if d is None else {k: (r3(d[k]) if isinstance(d.get(k), float) else d.get(k)) for k in keys if k in d}
+    roof = full.get("roofline") or {}
+    line = {k: full[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                                 "scaling", "vs_baseline", "dtype", "data", "config")}
+    line["value"], line["ms_per_step"] = r3(full["value"]) if full["value"] < 1e3 else round(full["value"], 1), round(full["ms_per_step"], 5)
+    line["timing"] = {"launch": full["launch"], "reps": full["reps"], "ms_per_step_min_max": [round(x, 5) for x in full["ms_per_step_min_max"]],
+                      "timed_ms_total": r3(full["timed_ms_total"]), "eager_ms_per_step": r3(full["eager"]["ms_per_step"]),
+                      "loss_fwd_bwd_ms": r3(full["loss_fwd_bwd_ms"]), "decode_nms_ms": r3(full["decode_nms_ms"]),
+                      "kernel_times": "cuda events around every launch of the eager pass (same K steps)"}
+    line["roofline"] = pick(roof, ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "share", "us",
+                                   "algorithmic_speedup", "what", "peak_source"))
+    line["hbm_kernels"] = {k: [r3(v["us"]), r3(v["frac"])] for k, v in (full.get("hbm_kernels") or {}).items()}
+    line["kernels_us"] = {k: r3(v["avg_ms"] * 1e3) for k, v in (full.get("kernels") or {}).items()}
+    cb = full.get("cpu_baseline")
+    line["cpu_baseline"] = None if cb is None else {"value": r3(cb.get("value")), "unit": cb.get("unit"), "cores": cb.get("cores"),
+                                                    "kind": cb.get("kind"), "sample": str(cb.get("sample"))[:160]}
+    tg = full.get("torch_gpu_baseline")
+    if tg:
+        line["torch_gpu_baseline"] = pick(tg, ("value", "unit", "loss_fwd_bwd_ms", "decode_nms_ms_per_image", "error"))
+    e2e_keys = ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "copy_ceiling", "frac_of_copy_ceiling", "api")
+    line["e2e"] = pick(full.get("e2e"), e2e_keys)
+    if full.get("e2e_labels"):
+        line["e2e_labels"] = pick(full["e2e_labels"], e2e_keys)
+    if full.get("e2e_graph"):
+        line["e2e_graph"] = pick(full["e2e_graph"], e2e_keys[:-1] + ("error",))
+    line["gpu_launches"] = full["gpu_launches"]
+    line["clocks"] = full["clocks"]
+    oc = full.get("other_configs") or {}
+    if oc:
+        line["configs"] = {k: (round(v["value"], 1) if v and "value" in v else None) for k, v in oc.items()}
+    if full.get("variants"):
+        line["variants"] = {k: round(v["decode_nms_images_per_s"], 1) for k, v in full["variants"].items()}
+    if full.get("dist_parity") is not None:
+        line["dist_parity"] = full["dist_parity"]
+    line["numa"] = full.get("numa")
+    line["full"] = "profiles/bench_last_full.json"
+    n = len(json.dumps(line, separators=(",", ":")))
+    for drop in ("kernels_us", "variants", "e2e_graph", "torch_gpu_baseline", "numa"):  # never exceed the driver's parse window
+        if n <= MAX_LINE_BYTES:
+            break
+        line.pop(drop, None)
+        n = len(json.dumps(line, separators=(",", ":")))
+    return line
+
+
+def check_dist_parity(yb, dev, rank, world, group):
+    """Outside every timed region: the sharded loss (one NCCL all-reduce of S*4 doubles) on a small fixed case
+    must equal the single-rank loss over the whole batch, values and gradient rows, on THIS hardware."""
+    import torch.distributed as dist
+    from yolo_from_scratch_b200 import dist as ybd
+    from yolo_from_scratch_b200 import ops
+    per, nc, img = 3, 3, 160
+    B = per * world
+    grids = [img // 8, img // 16, img // 32]
+    heads = make_heads(B, img, nc, 777)
+    labels = make_labels(np.random.default_rng(778), B, nc)
+    anchors = ops.default_anchors(dev)
+    lo, hi = ybd.shard_range(B, rank, world)
+    whole = [h.to(dev).requires_grad_(True) for h in heads]
+    tg = ops.build_targets(labels, anchors, grids, nc, img)
+    ref = ops.yolo_loss_multiscale(whole, tg, anchors, nc)
+    ref[0].backward()
+    mine = [h[lo:hi].to(dev).requires_grad_(True) for h in heads]
+    out = ybd.yolo_loss_multiscale_sharded(mine, [t[lo:hi].contiguous() for t in tg], anchors, nc, group=group)
+    out[0].backward()
+    rel = max(abs(float(a) - float(b)) / max(abs(float(b)), 1e-12) for a, b in zip(out, ref))
+    gerr = 0.0
+    for s in range(3):
+        want = whole[s].grad[lo:hi]
+        gerr = max(gerr, float((mine[s].grad - want).abs().max()) / max(float(want.abs().max()), 1e-30))
+    # and the label-list form (device-side assignment) on the same shard
+    mine2 = [h[lo:hi].to(dev).requires_grad_(True) for h in heads]
+    out2 = ops.yolo_loss_multiscale_labels(mine2, labels[lo:hi], anchors, nc, img, group=group)
+    rel = max(rel, max(abs(float(a) - float(b)) / max(abs(float(b)), 1e-12) for a, b in zip(out2, ref)))
+    t = torch.tensor([rel, gerr], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    rel, gerr = float(t[0]), float(t[1])
+    return {"max_rel_err": r3(rel), "grad_max_rel_err": r3(gerr), "ok": bool(rel <= 1e-5 and gerr <= 1e-5),
+            "case": f"{B} images sharded {per}/rank, nc={nc}, {img}^2, dense + label-list targets vs single-rank"}
+
+
+def timed_reps(run_steps, steps, reps, barrier, max_over_ranks):
+    """`reps` repetitions of: barrier+sync, event, K steps, event, barrier+sync.  Returns ms per step of every
+    repetition (max over ranks)."""
+    out = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        run_steps(steps)
+        e1.record()
+        barrier()
+        out.append(max_over_ranks(e0.elapsed_time(e1)) / steps)
+    return out
 
 
 def run_workload(args, rank, local_rank, world, dev, group, lib, full):
@@ -298,7 +546,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         packed = ops.pack_labels_host(labels, img, max_gt=MAX_GT)
         packed = ops.PackedLabels(packed[0].to(dev), packed[1].to(dev), packed[2].to(dev), img)
         dev_sets.append((d_heads, tg, packed))
-        if full:
+        if full and not args.no_e2e:
             host_sets.append(([h.pin_memory() for h in heads], [t.cpu().pin_memory() for t in tg]))
             label_sets.append(ops.pack_labels_host(labels, img, pin=True, max_gt=MAX_GT))
         del heads
@@ -321,7 +569,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident step ------------------------------------------------------------------
+    # ---- device-resident step, eager launches ----------------------------------------------------
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
     def step(i, conf=None, record=None):
@@ -338,7 +586,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
             record[2].record()
         return out4, det
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
     # candidate statistics per input set (outside the timed region)
@@ -362,10 +610,10 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         if st is not None:
             eval_counts.append(st[0])
             edge_counts.append(st[1])
+        del det
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # eager pass: K steps with a CUDA-event pair around every launch of the library (per-kernel times)
     lib.yb_timing_enable(1)
     launches0 = lib.yb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -375,16 +623,12 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
         step(i, record=ev[i])
     e1.record()
     barrier()
-    launches = lib.yb_launch_count() - launches0
+    eager_launches = lib.yb_launch_count() - launches0
     lib.yb_timing_enable(0)
-    sampler.stop_flag = True
-    sampler.join()
-    total_ms = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = total_ms / args.steps
-    loss_ms = float(np.mean([r[0].elapsed_time(r[1]) for r in ev]))
-    det_ms = float(np.mean([r[1].elapsed_time(r[2]) for r in ev]))
     buf = ctypes.create_string_buffer(1 << 16)
     lib.yb_timing_collect(buf, len(buf))
+    loss_ms = float(np.mean([r[0].elapsed_time(r[1]) for r in ev]))
+    det_ms = float(np.mean([r[1].elapsed_time(r[2]) for r in ev]))
     kernels = {}
     for ln in buf.value.decode().strip().splitlines():
         name, cnt, tot = ln.split()
@@ -393,50 +637,102 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     ksum = sum(k["ms_per_step"] for k in kernels.values())
     for k in kernels.values():
         k["share"] = k["ms_per_step"] / ksum if ksum else 0.0
+    # eager throughput without the event pairs
+    def eager_steps(n):
+        for i in range(n):
+            step(i)
 
-    # ---- the same device-resident step replayed as CUDA graphs (one graph per rotating input set) ----
-    graph_ms = graph_err = None
-    if full and args.launch == "graph":
-        try:
-            graph_ms = time_graph_replay(args, yb, dev_sets, anchors, layout, use_labels, n_sets, group, barrier,
-                                         max_over_ranks)
-        except Exception as e:  # pragma: no cover  (an optional leg must not lose the whole line)
-            graph_err = repr(e)
+    eager_reps = timed_reps(eager_steps, args.steps, max(1, min(args.reps, 3)), barrier, max_over_ranks)
+    eager_ms = float(np.median(eager_reps))
+
+    # ---- `value`: the same step replayed as CUDA graphs (one graph per rotating input set) -----------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    use_graph = args.launch == "graph"
+    graph_launches = None
+    if use_graph:
+        c0 = lib.yb_launch_count()
+        graphs = [yb.HotPathGraph(B, img, nc, anchors, args.conf, args.iou, max_gt=MAX_GT, layout=layout,
+                                  adopt_heads=ds[0], adopt_targets=ds[2] if use_labels else ds[1], group=group)
+                  for ds in dev_sets]
+        graph_launches = (lib.yb_launch_count() - c0) // (3 * n_sets)   # 2 warm-up passes + 1 capture per graph
+        for i in range(max(3, args.warmup)):
+            graphs[i % n_sets].replay()
+        sampler.samples.clear()
+        def graph_steps(n):
+            for i in range(n):
+                graphs[i % n_sets].replay()
+
+        reps_ms = timed_reps(graph_steps, args.steps, args.reps, barrier, max_over_ranks)
+        assert int(graphs[0].det["n_keep"].min()) >= 0
+        del graphs
+        torch.cuda.empty_cache()
+    else:
+        sampler.samples.clear()
+        reps_ms = timed_reps(eager_steps, args.steps, args.reps, barrier, max_over_ranks)
+    sampler.stop_flag = True
+    sampler.join()
+    step_ms = float(np.median(reps_ms))
+
+    # ---- a-1: decode_predictions forward / backward on the same heads (2T / 3T bytes) ---------------
+    decode = None
+    if full and layout == ops.LAYOUT_BHWAC:
+        decode = time_decode(lib, dev_sets, anchors, img, nc, n_sets, args.steps)
 
     # ---- e2e through the public API with host buffers ---------------------------------------------
     e2e = e2e_labels = e2e_graph = None
-    if full:
+    if full and not args.no_e2e:
+        ceil_dense = run_copy_ceiling(args, dev, world, host_sets, None, n_sets, barrier, max_over_ranks)
+        ceil_labels = run_copy_ceiling(args, dev, world, host_sets, label_sets, n_sets, barrier, max_over_ranks)
         e2e = run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier,
                       max_over_ranks)
         e2e_labels = run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier,
                              max_over_ranks, label_sets=label_sets)
+        for e, c in ((e2e, ceil_dense), (e2e_labels, ceil_labels)):
+            e["copy_ceiling"] = c["value"]
+            e["copy_ceiling_gbs_per_rank"] = c["h2d_gbs_per_rank"]
+            e["frac_of_copy_ceiling"] = e["value"] / c["value"]
         if world == 1:
             try:
                 e2e_graph = run_e2e_graph(args, yb, ops, dev, world, host_sets, label_sets, anchors, grids, n_sets,
                                           barrier, max_over_ranks)
+                e2e_graph["copy_ceiling"] = ceil_labels["value"]
+                e2e_graph["frac_of_copy_ceiling"] = e2e_graph["value"] / ceil_labels["value"]
             except Exception as e:  # pragma: no cover
-                e2e_graph = {"error": repr(e)}
+                e2e_graph = {"error": repr(e)[:200]}
 
     # ---- variants: other confidence thresholds (device-resident, detect only) ---------------------
     variants = {}
     if full and not args.no_variants and rank == 0:
+        import gc
+        gc.collect()              # the e2e legs' CUDA graphs and pools are released here, not inside a timed loop
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
         for conf in (0.25, 0.001):
-            for i in range(3):  # detect only: rank 0 runs this alone, so no collective may be enqueued here
+            for i in range(4):  # detect only: rank 0 runs this alone, so no collective may be enqueued here
                 ops.detect_batch(dev_sets[i % n_sets][0], anchors, img, nc, conf, args.iou, layout=layout)
             torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             n_it = max(5, args.steps // 3)
-            a.record()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_it + 1)]
+            evs[0].record()
             for i in range(n_it):
                 heads = dev_sets[i % n_sets][0]
                 det = ops.detect_batch(heads, anchors, img, nc, conf, args.iou, layout=layout)
-            b.record()
+                evs[i + 1].record()
             torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / n_it
+            ms = float(np.median([evs[i].elapsed_time(evs[i + 1]) for i in range(n_it)]))
             variants[f"conf_{conf}"] = {"decode_nms_ms": ms, "decode_nms_images_per_s": B / (ms * 1e-3),
                                         "candidates_per_image": float(det["counts"].double().mean()),
                                         "kept_per_image": float(det["n_keep"].double().mean())}
+            del det
     barrier()
+
+    torch_gpu = None
+    if full and world == 1 and rank == 0 and not args.no_torch_gpu_baseline:
+        try:
+            torch_gpu = run_torch_gpu_reference(args, dev, min(B, 8))
+        except Exception as e:  # pragma: no cover
+            torch_gpu = {"error": repr(e)[:200]}
 
     if rank != 0:
         return None
@@ -446,7 +742,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(
@@ -460,123 +756,150 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
     pos = float(np.mean([sum(float((t[..., 4] > 0.5).sum()) for t in ds[1]) for ds in dev_sets]))
     M_tot = float(np.mean(cand_counts))
     sector = min(row_bytes, 32)
+    obj_read = rows * (4 if args.layout == "nchw" else sector)
     alg_bytes = {
         # T (dense grad write) + obj sectors of pred and target + positive rows of pred and target
         "loss_main_kernel": T_bytes + (1 if use_labels else 2) * rows * sector + 2 * pos * row_bytes,
         # NCHW: the objectness logits are contiguous planes (4 B per row); dense targets keep their sectors
         "loss_main_nchw_kernel": T_bytes + rows * 4 + (rows / 8 if use_labels else rows * sector),
-        # objectness sector of every row
-        "filter_count_kernel": rows * (4 if args.layout == "nchw" else sector),
-        # objectness sector of every row again + the candidate rows + 28 B of output per candidate
-        "filter_emit_kernel": rows * (4 if args.layout == "nchw" else sector) + M_tot * row_bytes + 28 * M_tot,
+        # two-pass filter: objectness sector of every row, then again + the candidate rows + 28 B of output per candidate
+        "filter_count_kernel": obj_read,
+        "filter_emit_kernel": obj_read + M_tot * row_bytes + 28 * M_tot,
+        # one-pass filter: every objectness sector once + candidate rows + outputs
+        "filter_onepass_kernel": obj_read + M_tot * max(row_bytes - sector, 0) + 28 * M_tot,
     }
     hbm_kernels = {}
     for name, a_bytes in alg_bytes.items():
         if name in kernels:
             ach = a_bytes / (kernels[name]["avg_ms"] * 1e-3) / 1e9
-            hbm_kernels[name] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": ach / hbm_peak, "algorithmic_bytes": a_bytes, "share": kernels[name]["share"],
-                                 "traffic": traffic.get(name)}
-    # ---- NMS: pair throughput against the fp32 issue rate ---------------------------------------------
+            hbm_kernels[name] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                 "us": kernels[name]["avg_ms"] * 1e3, "algorithmic_bytes": a_bytes,
+                                 "share": kernels[name]["share"], "traffic": traffic.get(name), "peak_source": peak_src}
+    if decode:
+        for name, (ms, nbytes) in decode.items():
+            ach = nbytes / (ms * 1e-3) / 1e9
+            hbm_kernels[name] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                 "us": ms * 1e3, "algorithmic_bytes": nbytes, "share": None, "traffic": traffic.get(name),
+                                 "peak_source": peak_src}
+    # ---- NMS: executed IoU pair tests against the fp32 issue rate --------------------------------------
     pairs = float(np.mean(pair_counts))
     issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / 17.0 / 1e9  # Gpair/s at 17 warp-instructions per 32 pairs
     nms_ms = sum(kernels[k]["ms_per_step"] for k in kernels if k.startswith(("graph_", "nms_")))
     nms_roof = {}
     if "graph_edge_kernel" in kernels:
         ek = kernels["graph_edge_kernel"]
-        evald = float(np.mean(eval_counts)) if eval_counts else None  # pair tests (yb_nms_graph_stats)
+        evald = float(np.mean(eval_counts)) if eval_counts else None  # pair tests executed (yb_nms_graph_stats)
+        ach = (evald / (ek["avg_ms"] * 1e-3) / 1e9) if evald else None
         nms_roof = {
             "kernel": "graph_edge_kernel", "bound": "fp32-issue", "unit": "Gpair/s", "peak": issue_peak,
-            "peak_source": "148 SM x 4 schedulers x 32 lanes x sampled SM clock / 17 warp-instructions per 32 exact "
-                           "IoU>thr tests (SASS of the dense bitmask kernel): the rate at which ALL pairs could be tested",
-            # algorithmic work: the pairs torchvision's kernel evaluates, M(M-1)/2 per image
-            # (same-class pairs in the per-class regime), per launch, over the kernel's measured duration
-            "algorithmic_pairs_per_launch": pairs,
-            "achieved": pairs / (ek["avg_ms"] * 1e-3) / 1e9,
-            "frac": pairs / (ek["avg_ms"] * 1e-3) / 1e9 / issue_peak,
-            "frac_note": "above 1 because the graph algorithm culls pairs by tile statistics instead of testing them",
-            # what the kernel really tests, and how much of the issue rate those tests use
+            "peak_source": "148 SM x 4 schedulers x 32 lanes x sampled SM clock / 17 warp-instr per 32 exact IoU>thr tests "
+                           "(SASS of the dense bitmask kernel)",
+            "what": "IoU pair tests EXECUTED per launch / launch time; the pairs the graph algorithm culls are in algorithmic_speedup",
+            "achieved": ach, "frac": (ach / issue_peak) if ach else None,
             "evaluated_pairs_per_launch": evald,
+            "algorithmic_pairs_per_launch": pairs,          # what torchvision's kernel evaluates: M(M-1)/2 per image
+            "algorithmic_speedup": (pairs / evald) if evald else None,
+            "algorithmic_gpairs": pairs / (ek["avg_ms"] * 1e-3) / 1e9,
             "edges_per_launch": float(np.mean(edge_counts)) if edge_counts else None,
-            "evaluated_gpairs": (evald / (ek["avg_ms"] * 1e-3) / 1e9) if evald else None,
-            "evaluated_frac_of_peak": (evald / (ek["avg_ms"] * 1e-3) / 1e9 / issue_peak) if evald else None,
-            # all algorithmic pairs per second of the whole NMS (sort + gather + edges + resolve)
             "whole_nms_algorithmic_gpairs": pairs / (nms_ms * 1e-3) / 1e9 if nms_ms else None,
-            "share": ek["share"], "traffic": traffic.get("graph_edge_kernel"),
+            "us": ek["avg_ms"] * 1e3, "share": ek["share"], "traffic": traffic.get("graph_edge_kernel"),
         }
     dominant = max(kernels, key=lambda k: kernels[k]["share"]) if kernels else None
     if dominant in hbm_kernels:
-        roofline = dict(hbm_kernels[dominant], kernel=dominant, peak_source=peak_src)
+        roofline = dict(hbm_kernels[dominant], kernel=dominant)
     elif dominant == "graph_edge_kernel":
         roofline = dict(nms_roof)
-        roofline["note"] = ("dominant kernel is the NMS edge discovery: SIMT fp32 compare/min/max work, no HBM or "
-                            "tensor bound applies (north_star: IoU pair-throughput for NMS); HBM-bound kernels are "
-                            "under hbm_kernels")
     else:
         roofline = {"kernel": dominant, "bound": "latency", "achieved": None, "peak": None, "frac": None,
-                    "share": kernels[dominant]["share"] if dominant else None}
-    for v in hbm_kernels.values():
-        v["peak_source"] = peak_src
+                    "share": kernels[dominant]["share"] if dominant else None,
+                    "us": kernels[dominant]["avg_ms"] * 1e3 if dominant else None}
 
-    cpu_baseline = torch_gpu = None
-    if full and world == 1 and not args.no_cpu_baseline:
-        v, ms, cores, sample = run_cpu_reference(args, min(B, 8), 2, 1)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
-    if full and world == 1 and not args.no_torch_gpu_baseline:
-        try:
-            torch_gpu = run_torch_gpu_reference(args, dev, min(B, 8))
-        except Exception as e:  # pragma: no cover
-            torch_gpu = {"error": repr(e)}
-
-    eager = {"value": B * world / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "unit": UNIT,
-             "what": "the same K steps with eager launches (one launch per kernel from Python/ctypes)"}
-    use_graph = graph_ms is not None
-    step_ms = graph_ms if use_graph else ms_per_step
-    line = {
+    result = {
         "metric": METRIC, "value": B * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-        "launch": ("cuda-graph replay (yb.HotPathGraph, one graph per rotating input set" +
-                   (", NCCL all-reduce captured inside" if world > 1 else "") + ")") if use_graph else "eager",
-        "eager": eager,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world, n_sets),
-        "graph_replay": ({"error": graph_err} if graph_err else None) if graph_ms is None else {
-            "ms_per_step": graph_ms, "value": B * world / (graph_ms * 1e-3), "unit": UNIT,
-            "what": "the device-resident step (loss fwd+bwd, decode+filter+NMS, plus detection packing) replayed as one "
-                    "CUDA graph per input set: launch gaps removed"},
+        "launch": ("cuda-graph replay (HotPathGraph per input set" + (", NCCL all-reduce captured inside)" if world > 1 else ")"))
+                  if use_graph else "eager",
+        "reps": args.reps, "ms_per_step_reps": reps_ms, "ms_per_step_min_max": [min(reps_ms), max(reps_ms)],
+        "timed_ms_total": float(sum(reps_ms)) * args.steps,
+        "eager": {"value": B * world / (eager_ms * 1e-3), "ms_per_step": eager_ms, "unit": UNIT, "reps_ms": eager_reps,
+                  "what": "the same K steps with eager launches (one launch per kernel from Python/ctypes)"},
         "loss_fwd_bwd_ms": loss_ms, "decode_nms_ms": det_ms, "decode_nms_images_per_s": B * world / (det_ms * 1e-3),
         "candidates_per_image": float(np.mean(cand_counts)) / B, "kept_per_image": float(np.mean(keep_counts)) / B,
-        "e2e": e2e, "e2e_labels": e2e_labels, "e2e_graph": e2e_graph, "gpu_launches": int(launches),
-        "gpu_launches_note": "kernels of libyolo_b200.so enqueued during the K eager steps (the per-kernel table); a graph "
-                             "replay runs the same kernels plus pack_kernel from one cudaGraphLaunch",
-        "kernels": kernels,
-        "roofline": roofline, "hbm_kernels": hbm_kernels, "roofline_nms": nms_roof, "cpu_baseline": cpu_baseline,
-        "torch_gpu_baseline": torch_gpu, "clocks": clocks, "variants": variants,
+        "e2e": e2e, "e2e_labels": e2e_labels, "e2e_graph": e2e_graph,
+        # kernels of libyolo_b200.so that execute inside ONE K-step timed region
+        "gpu_launches": int((graph_launches if use_graph else eager_launches / args.steps) * args.steps),
+        "gpu_launches_note": "kernels of libyolo_b200.so per K-step timed region: counted at graph capture (replays re-run them) "
+                             "or, eager, by the library's launch counter",
+        "kernels": kernels, "roofline": roofline, "hbm_kernels": hbm_kernels, "roofline_nms": nms_roof,
+        "cpu_baseline": None, "torch_gpu_baseline": torch_gpu, "clocks": clocks, "variants": variants,
     }
     del dev_sets, host_sets
-    return line
+    return result
 
 
-def time_graph_replay(args, yb, dev_sets, anchors, layout, use_labels, n_sets, group, barrier, max_over_ranks):
-    """ms per device-resident step when the step is replayed as CUDA graphs, one per rotating input set
-    (max over ranks; with a process group the loss all-reduce is captured inside the graphs)."""
-    graphs = [yb.HotPathGraph(args.batch, args.img, args.nc, anchors, args.conf, args.iou, max_gt=MAX_GT, layout=layout,
-                              adopt_heads=ds[0], adopt_targets=ds[2] if use_labels else ds[1], group=group)
-              for ds in dev_sets]
-    for i in range(max(3, args.warmup)):
-        graphs[i % n_sets].replay()
+def time_decode(lib, dev_sets, anchors, img, nc, n_sets, steps):
+    """decode_predictions forward and backward (a-1) over the three heads, CUDA events on the launching stream,
+    rotating input sets.  Returns {name: (ms per pass over all scales, algorithmic bytes)}."""
+    st = torch.cuda.current_stream().cuda_stream
+    outs = [[torch.empty_like(h) for h in ds[0]] for ds in dev_sets[:2]]
+    T = tensor_bytes(dev_sets[0][0])
+
+    def fwd(i):
+        for s, h in enumerate(dev_sets[i % n_sets][0]):
+            B, H, W, A, row = h.shape
+            lib.yb_decode_fwd(h.data_ptr(), anchors[s].data_ptr(), outs[i % 2][s].data_ptr(), B, H, W, A, row - 5, float(img), st)
+
+    def bwd(i):
+        for s, h in enumerate(dev_sets[i % n_sets][0]):
+            B, H, W, A, row = h.shape
+            lib.yb_decode_bwd(h.data_ptr(), anchors[s].data_ptr(), dev_sets[(i + 1) % n_sets][0][s].data_ptr(),
+                              outs[i % 2][s].data_ptr(), B, H, W, A, row - 5, float(img), st)
+    res = {}
+    for name, fn, nbytes in (("decode_fwd(3 scales)", fwd, 2 * T), ("decode_bwd(3 scales)", bwd, 3 * T)):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        res[name] = (a.elapsed_time(b) / steps, nbytes)
+    return res
+
+
+def run_copy_ceiling(args, dev, world, host_sets, label_sets, n_sets, barrier, max_over_ranks):
+    """The host->device ceiling of the e2e legs: the same pinned buffers copied into device buffers, no kernels,
+    every rank at once, K steps."""
+    slots = []
+    for k in range(2):
+        heads_d = [torch.empty_like(h, device=dev) for h in host_sets[0][0]]
+        if label_sets is None:
+            extra = [torch.empty_like(t, device=dev) for t in host_sets[0][1]]
+        else:
+            extra = [torch.empty_like(t, device=dev) for t in label_sets[0]]
+        slots.append((heads_d, extra))
+    nbytes = tensor_bytes(slots[0][0]) + tensor_bytes(slots[0][1])
+
+    def run(n):
+        for i in range(n):
+            hd, ex = slots[i % 2]
+            for d, h in zip(hd, host_sets[i % n_sets][0]):
+                d.copy_(h, non_blocking=True)
+            for d, h in zip(ex, host_sets[i % n_sets][1] if label_sets is None else label_sets[i % n_sets]):
+                d.copy_(h, non_blocking=True)
+    run(3)
     barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for i in range(args.steps):
-        graphs[i % n_sets].replay()
-    g1.record()
+    t0 = time.perf_counter()
+    run(args.steps)
+    torch.cuda.synchronize()
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     barrier()
-    ms = max_over_ranks(g0.elapsed_time(g1)) / args.steps
-    assert int(graphs[0].det["n_keep"].min()) >= 0
-    del graphs
-    torch.cuda.empty_cache()
-    return ms
+    return {"value": args.batch * world / (ms * 1e-3), "ms_per_step": ms, "h2d_bytes_per_step": nbytes,
+            "h2d_gbs_per_rank": nbytes / (ms * 1e-3) / 1e9}
 
 
 def run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids, n_sets, barrier, max_over_ranks,
@@ -652,6 +975,8 @@ def run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids
         sl = slots[i % n_slots]
         sl["off_ready"].synchronize()                  # host needs the row count; step i+1's H2D is in flight
         n = int(sl["off_host"][-1])
+        if n < 0:
+            raise RuntimeError("NMS reported a failed image")
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(sl["off_ready"])
             sl["det_host"][:n].copy_(sl["rows_d"][:n], non_blocking=True)
@@ -684,12 +1009,11 @@ def run_e2e(args, yb, ops, dev, group, world, host_sets, anchors, weights, grids
     wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
     e2e_ms = max_over_ranks(wall_ms) / args.steps
-    api = ("yolo_loss_multiscale_labels(heads, packed labels)" if label_sets is not None
+    api = ("yolo_loss_multiscale_labels(heads, label lists)" if label_sets is not None
            else "yolo_loss_multiscale(heads, dense targets)")
     return {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(np.mean(d2h_acc)),
-            "api": api + ".backward() + detect_batch + pack_detections; pinned host tensors, H2D / compute / D2H "
-                   "pipelined over 3 input slots, timed by host wall clock around all steps"}
+            "api": api + ".backward()+detect_batch+pack_detections; pinned host in/out, 3-slot pipeline, host wall clock"}
 
 
 def run_e2e_graph(args, yb, ops, dev, world, host_sets, label_sets, anchors, grids, n_sets, barrier, max_over_ranks):
@@ -739,6 +1063,8 @@ def run_e2e_graph(args, yb, ops, dev, world, host_sets, label_sets, anchors, gri
         sl = slots[i % n_slots]
         sl["off_ready"].synchronize()
         n = int(sl["off_host"][-1])
+        if n < 0:
+            raise RuntimeError("NMS reported a failed image")
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(sl["off_ready"])
             sl["det_host"][:n].copy_(sl["hp"].rows[:n], non_blocking=True)
@@ -775,9 +1101,10 @@ def run_e2e_graph(args, yb, ops, dev, world, host_sets, label_sets, anchors, gri
 
 
 def run_torch_gpu_reference(args, dev, sample_images):
-    """The reference's GPU-PyTorch path (north_star's comparison point): the oracle port of train.py's
-    loss (:840-886, autograd backward) and of predict()'s per-image decode/filter + torchvision's CUDA
-    batched_nms (:1152-1238), run on CUDA tensors.  Reported only; not on the product path."""
+    """The reference's GPU-PyTorch path (north_star's comparison point): train.py's loss (:840-886, autograd
+    backward) and predict()'s per-image decode/filter + torchvision's CUDA batched_nms (:1152-1238) on CUDA
+    tensors — the unmodified reference functions when baseline/_ref is staged, else the oracle port.
+    Reported only; not on the product path."""
     from oracle import ref_path as R
     import torchvision
     B, img, nc = args.batch, args.img, args.nc
@@ -787,10 +1114,12 @@ def run_torch_gpu_reference(args, dev, sample_images):
     grids = [img // 8, img // 16, img // 32]
     tg = [R.assign_targets(l, R.default_anchors(), grids, nc, img) for l in labels]
     tgts = [torch.from_numpy(np.stack([t[s] for t in tg])).to(dev) for s in range(3)]
+    ref = load_unmodified_reference()
+    loss_fn = ref.yolo_loss_multiscale if ref is not None else R.multiscale_loss
 
     def loss_step():
         preds = [h.clone().requires_grad_(True) for h in heads]
-        R.multiscale_loss(preds, tgts, anchors, nc)[0].backward()
+        loss_fn(preds, tgts, anchors, nc)[0].backward()
 
     def det_step(n_img):
         kept = 0
@@ -817,8 +1146,10 @@ def run_torch_gpu_reference(args, dev, sample_images):
     det_ms = timed(lambda: det_step(sample_images), 3)  # sample_images images
     per_image_ms = loss_ms / B + det_ms / sample_images
     return {"value": 1e3 / per_image_ms, "unit": UNIT, "loss_fwd_bwd_ms": loss_ms,
-            "decode_nms_ms_per_image": det_ms / sample_images, "kind": "port on CUDA tensors (torch eager + "
-            "torchvision CUDA nms)", "sample": f"loss on all {B} images, decode+NMS on {sample_images} of {B} images"}
+            "decode_nms_ms_per_image": det_ms / sample_images,
+            "kind": ("unmodified reference loss" if ref is not None else "port loss") + " + port of predict()'s body on CUDA tensors "
+                    "(torch eager + torchvision CUDA nms)",
+            "sample": f"loss on all {B} images, decode+NMS on {sample_images} of {B} images"}
 
 
 def main():
@@ -832,9 +1163,6 @@ def main():
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     b200_main(args, rank, local_rank, world)
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

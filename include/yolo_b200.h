@@ -209,8 +209,9 @@ int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const float* let
  *   algo selects how the same result is computed:
  *     YB_NMS_GRAPH    (default) sparse suppression graph: spatial/area-ordered tile culling, edge
  *                     list, parallel fixed-point resolve.  Workspace holds the edge list; an image
- *                     with more edges than fit (or class ids >= 512) reports n_keep[b] = -1 and
- *                     should be re-run with YB_NMS_BITMASK.
+ *                     with more edges than fit (heavily clustered boxes) or class ids >= 512 is
+ *                     resolved inside the same launch by a blocked greedy pass (M x kept pair
+ *                     tests, exact arithmetic), so n_keep[b] is never negative for this algorithm.
  *     YB_NMS_BITMASK  dense blocked IoU bitmask + serial scan (torchvision's structure, batched);
  *                     class ids < 65536; never overflows with yb_nms_workspace_bytes().
  * ---------------------------------------------------------------------------------------- */
@@ -234,6 +235,8 @@ int yb_nms_graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned
  *   Packs the kept detections of a batch as rows (x1, y1, x2, y2, conf, class) fp32, image after
  *   image, each image in descending score order.  out must hold sum(n_keep)*6 floats
  *   (<= B*cap*6); offsets (B+1) int32 receives the first row of every image and the total.
+ *   If any n_keep[b] is negative (NMS reported a failure for that image) the total offsets[B] is -1:
+ *   a failed image never reads as "no detections".
  * ---------------------------------------------------------------------------------------- */
 int yb_pack_detections(const float* boxes, const float* scores, const int64_t* classes,
                        const int64_t* keep, const int* n_keep, int B, int cap, float* out,

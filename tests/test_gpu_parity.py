@@ -359,6 +359,74 @@ def test_nchw_heads_give_identical_results(yb, B, nc, grids, img):
             assert torch.equal(d0["keep"][b, :k], d1["keep"][b, :k])
 
 
+@pytest.mark.parametrize("B,nc,grids,img", [(2, 1, (40, 20, 10), 320), (2, 80, (20, 10, 5), 160), (3, 3, (13, 7, 5), 104)])
+def test_nchw_heads_against_the_oracle(yb, B, nc, grids, img):
+    """f-2 against the oracle itself (not against the BHWAC CUDA path): losses, gradients (permuted to NCHW),
+    candidates and keep sets of the *_nchw entry points equal the CPU restatement of the reference, for dense
+    targets, label lists and PackedLabels."""
+    from yolo_from_scratch_b200 import ops
+    g = torch.Generator().manual_seed(41 + nc)
+    raw = [torch.randn(B, 3 * (5 + nc), G, G, generator=g) for G in grids]
+    heads = [r.view(B, 3, 5 + nc, G, G).permute(0, 3, 4, 1, 2).contiguous() for r, G in zip(raw, grids)]  # train.py:608-609
+    labels = _random_labels(np.random.default_rng(nc + 5), B, nc, 20)
+    tg = [torch.from_numpy(np.stack([R.assign_targets(l, ANCH, list(grids), nc, img)[s] for l in labels])) for s in range(3)]
+    cp = [h.clone().requires_grad_(True) for h in heads]
+    ref = R.multiscale_loss(cp, tg, ANCH, nc)
+    ref[0].backward()
+    to_nchw = lambda t: t.permute(0, 3, 4, 1, 2).reshape(t.shape[0], -1, t.shape[1], t.shape[2])
+    for targets in ([t.cuda() for t in tg], labels, ops.pack_labels(labels, img)):
+        xp = [r.clone().cuda().requires_grad_(True) for r in raw]
+        out = yb.yolo_loss_multiscale_nchw(xp, targets, ANCH, nc, img)
+        out[0].backward()
+        for a, b in zip(out, ref):
+            close(a, b, rtol=RTOL, atol=1e-7)
+        for x, c in zip(xp, cp):
+            grad_close(x.grad, to_nchw(c.grad))
+    for conf in (0.5, 0.05):
+        det = yb.detect_batch_nchw([r.cuda() for r in raw], ANCH, img, nc, conf, 0.4)
+        counts, n_keep = det["counts"].cpu(), det["n_keep"].cpu()
+        for b in range(B):
+            rb, rs, rc = R.candidates([h[b:b + 1] for h in heads], ANCH, img, nc, conf)
+            m = int(counts[b])
+            bx, sc, cl = (det[k][b, :m].cpu().numpy() for k in ("boxes", "scores", "classes"))
+            assert m == rb.shape[0] and np.array_equal(cl, rc.numpy())
+            assert np.allclose(bx, rb.numpy(), rtol=1e-5, atol=1e-4) and np.allclose(sc, rs.numpy(), rtol=1e-5, atol=1e-7)
+            want = R.batched_nms_indices(bx, sc, cl, 0.4, arith="cuda", device_rule="cuda")
+            assert np.array_equal(det["keep"][b, :int(n_keep[b])].cpu().numpy(), want)
+
+
+def test_loss_second_backward_with_retain_graph(yb):
+    """backward twice through the same graph (retain_graph=True, which the reference loss supports)
+    gives the reference's accumulated gradient, also with an upstream factor != 1."""
+    B, nc, grids, img = 2, 2, (8, 4, 2), 64
+    g = torch.Generator().manual_seed(9)
+    heads = [torch.randn(B, G, G, 3, 5 + nc, generator=g) for G in grids]
+    labels = _random_labels(np.random.default_rng(9), B, nc, 6)
+    tg = yb.build_targets(labels, ANCH, list(grids), nc, img)
+    xp = [h.clone().cuda().requires_grad_(True) for h in heads]
+    out = yb.yolo_loss_multiscale(xp, tg, ANCH, nc)
+    (out[0] * 3.0).backward(retain_graph=True)
+    (out[0] * 3.0).backward()
+    cp = [h.clone().requires_grad_(True) for h in heads]
+    ref = R.multiscale_loss(cp, [t.cpu() for t in tg], ANCH, nc)
+    (ref[0] * 6.0).backward()
+    for x, c in zip(xp, cp):
+        grad_close(x.grad, c.grad)
+
+
+def test_label_list_check_flag(yb):
+    """the label-list wrappers raise like the reference (IndexError) when asked to check."""
+    nc, img, grids = 1, 64, (8, 4, 2)
+    heads = [torch.randn(1, G, G, 3, 6).cuda() for G in grids]
+    bad = [np.array([[0, -1.5, 0.5, 0.1, 0.1]])]
+    with pytest.raises(IndexError):
+        yb.yolo_loss_multiscale_labels(heads, bad, ANCH, nc, img, check=True)
+    raw = [h.permute(0, 3, 4, 1, 2).reshape(1, -1, h.shape[1], h.shape[2]).contiguous() for h in heads]
+    with pytest.raises(IndexError):
+        yb.yolo_loss_multiscale_nchw(raw, bad, ANCH, nc, img, check=True)
+    yb.yolo_loss_multiscale_labels(heads, [np.array([[0, .5, .5, .1, .1]])], ANCH, nc, img, check=True)
+
+
 # ---- CUDA-graph step ------------------------------------------------------------------------------------
 @pytest.mark.parametrize("targets,layout", [("labels", 0), ("dense", 0), ("labels", 1)])
 def test_hot_path_graph_replays_equal_eager(yb, targets, layout):
@@ -673,16 +741,123 @@ def test_nms_clustered_detections(yb, n, algo):
     assert np.array_equal(got, R.nms_indices(boxes.numpy(), scores.numpy(), 0.45, "cuda"))
 
 
-def test_nms_graph_overflow_falls_back_to_bitmask(yb):
-    """3000 identical boxes: 4.5M edges do not fit the default edge list -> n_keep = -1 from the
-    graph algorithm, transparently re-run on the dense bitmask algorithm."""
+def test_nms_graph_overflow_resolved_on_device(yb):
+    """3000 identical boxes: 4.5M edges do not fit the default edge list.  The graph algorithm resolves
+    the image inside the same launch (blocked greedy pass): no n_keep = -1, no host round trip."""
     n = 3000
     boxes = torch.tensor([[10.0, 10.0, 50.0, 60.0]]).repeat(n, 1)
     scores = torch.rand(n, generator=torch.Generator().manual_seed(3))
     keep, n_keep = yb.batched_nms_padded(boxes.cuda().unsqueeze(0), scores.cuda().unsqueeze(0), None, None, 0.5)
-    assert int(n_keep[0]) == -1
-    got = yb.nms(boxes.cuda(), scores.cuda(), 0.5).cpu().numpy()
-    assert np.array_equal(got, R.nms_indices(boxes.numpy(), scores.numpy(), 0.5, "cuda")) and len(got) == 1
+    want = R.nms_indices(boxes.numpy(), scores.numpy(), 0.5, "cuda")
+    assert int(n_keep[0]) == 1 == len(want)
+    assert np.array_equal(keep[0, :1].cpu().numpy(), want)
+    assert np.array_equal(yb.nms(boxes.cuda(), scores.cuda(), 0.5).cpu().numpy(), want)
+
+
+def _clusters(n_clusters, per, n_cls, seed, span=600.0, neg=False):
+    """A trained detector at a low confidence threshold: tight clusters of jittered boxes around objects."""
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(n_clusters, 2, generator=g) * span - (200.0 if neg else 0.0)
+    wh = torch.rand(n_clusters, 2, generator=g) * 120.0 + 20.0
+    cc = c[:, None, :] + torch.randn(n_clusters, per, 2, generator=g) * 4.0
+    ww = wh[:, None, :] * (1.0 + 0.15 * torch.randn(n_clusters, per, 2, generator=g)).clamp(0.3, 2.0)
+    boxes = torch.cat([cc - ww / 2, cc + ww / 2], dim=2).reshape(-1, 4)
+    cls = torch.randint(0, n_cls, (n_clusters, 1), generator=g).repeat(1, per)
+    flip = torch.rand(n_clusters, per, generator=g) < 0.2
+    cls = torch.where(flip, torch.randint(0, n_cls, (n_clusters, per), generator=g), cls).reshape(-1)
+    scores = torch.rand(boxes.shape[0], generator=g)
+    scores[::11] = scores[0]
+    return boxes, scores, cls
+
+
+@pytest.mark.parametrize("mode,n_cls", [("plain", 1), ("trick", 7), ("class", 7), ("trick_neg", 5), ("bigcls", 3000)])
+def test_nms_greedy_fallback_is_exact(yb, monkeypatch, mode, n_cls):
+    """Force the on-device fallback (edge list of 1 edge per box on clustered boxes; class ids >= 512) and
+    compare with torchvision's CUDA kernels and the C oracle, in every batched_nms regime."""
+    import torchvision
+    from yolo_from_scratch_b200 import ops
+    if mode != "bigcls":
+        monkeypatch.setattr(ops, "GRAPH_EDGES_PER_BOX", 1)
+    B = 3
+    cases = [_clusters(50, 90 + 10 * b, n_cls, 100 + b, neg=(mode == "trick_neg")) for b in range(B)]
+    cap = max(c[0].shape[0] for c in cases)
+    boxes = torch.zeros(B, cap, 4); scores = torch.zeros(B, cap); classes = torch.zeros(B, cap, dtype=torch.int64)
+    counts = torch.zeros(B, dtype=torch.int32)
+    for b, (bx, sc, cl) in enumerate(cases):
+        m = bx.shape[0]
+        boxes[b, :m], scores[b, :m], classes[b, :m], counts[b] = bx, sc, cl, m
+    trick = -1 if mode == "class" else (1 << 40)
+    cls_arg = None if mode == "plain" else classes.cuda()
+    keep, n_keep, ws = yb.batched_nms_padded(boxes.cuda(), scores.cuda(), cls_arg, counts.cuda(), 0.4, trick,
+                                             return_workspace=True)
+    for b, (bx, sc, cl) in enumerate(cases):
+        got = keep[b, :int(n_keep[b])].cpu().numpy()
+        if mode == "plain":
+            want_tv = torchvision.ops.nms(bx.cuda(), sc.cuda(), 0.4).cpu().numpy()
+            want = R.nms_indices(bx.numpy(), sc.numpy(), 0.4, "cuda")
+        elif mode == "class":
+            want_tv = torchvision.ops.boxes._batched_nms_vanilla(bx.cuda(), sc.cuda(), cl.cuda(), 0.4).cpu().numpy()
+            want = None
+        else:
+            want_tv = torchvision.ops.boxes._batched_nms_coordinate_trick(bx.cuda(), sc.cuda(), cl.cuda(), 0.4).cpu().numpy()
+            want = None
+        assert int(n_keep[b]) >= 0
+        assert np.array_equal(got, want_tv), (mode, b, len(got), len(want_tv))
+        if want is not None:
+            assert np.array_equal(got, want)
+    if mode != "bigcls":   # the edge list really overflowed: more edges than its capacity of 1 per box
+        ev, ed = ctypes_stats(yb, ws, B, cap)
+        assert ed > B * cap
+
+
+def ctypes_stats(yb, ws, B, cap):
+    import ctypes
+    ev, ed = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    yb._lib.check(yb._lib.lib().yb_nms_graph_stats(ws.data_ptr(), ws.numel(), B, cap, ctypes.byref(ev), ctypes.byref(ed),
+                                                   torch.cuda.current_stream().cuda_stream), "stats")
+    return int(ev.value), int(ed.value)
+
+
+def test_hot_path_graph_with_overflowing_images(yb):
+    """on the CUDA-graph path an image whose suppression graph overflows the edge list must
+    come back with the oracle's keep set, not with zero detections.  Heads with huge, heavily overlapping boxes
+    (tw = th = +6: 4x the anchor) and every row above the confidence threshold."""
+    from yolo_from_scratch_b200 import ops
+    B, nc, img, grids = 3, 1, 160, (20, 10, 5)
+    hp = yb.HotPathGraph(B, img, nc, ANCH, conf_threshold=0.3, iou_threshold=0.4, max_gt=4, targets="labels")
+    g = torch.Generator().manual_seed(5)
+    heads = [torch.randn(B, G, G, 3, 6, generator=g) for G in grids]
+    for h in heads:
+        h[0, ..., 2:4] = 6.0      # image 0: every box 4x its anchor -> dense graph
+        h[0, ..., 4] = 3.0
+        h[2, ..., 2:4] = 5.0
+        h[2, ..., 4] = 2.0
+    for dst, src in zip(hp.heads, heads):
+        dst.copy_(src.cuda())
+    for _ in range(2):
+        _, _, det = hp.replay()
+    torch.cuda.synchronize()
+    counts, n_keep = det["counts"].cpu(), det["n_keep"].cpu()
+    ev, ed = ctypes_stats(yb, det["nms_ws"], B, det["boxes"].shape[1])
+    assert ed > ops.GRAPH_EDGES_PER_BOX * int(counts[0])        # image 0 alone overflows its edge list
+    off = hp.offsets.cpu()
+    assert int(off[-1]) == int(n_keep.sum()) and (n_keep > 0).all()
+    for b in range(B):
+        m = int(counts[b])
+        bx, sc, cl = (det[k][b, :m].cpu().numpy() for k in ("boxes", "scores", "classes"))
+        want = R.batched_nms_indices(bx, sc, cl, 0.4, arith="cuda", device_rule="cuda")
+        assert np.array_equal(det["keep"][b, :int(n_keep[b])].cpu().numpy(), want), b
+
+
+def test_pack_reports_a_failed_image(yb):
+    """pack_detections never turns n_keep = -1 into "no detections": the total becomes -1 and
+    detections_to_lists raises.  (Only the bitmask algorithm with an undersized workspace can produce -1.)"""
+    det = yb.detect_batch([torch.randn(2, G, G, 3, 6).cuda() for G in (8, 4, 2)], ANCH, 64, 1, 0.3, 0.4)
+    det["n_keep"][1] = -1
+    rows, offsets = yb.pack_detections(det)
+    assert int(offsets[-1]) == -1
+    with pytest.raises(RuntimeError):
+        yb.detections_to_lists(det)
 
 
 # ---- end to end: the reference's predict() goldens ----------------------------------------------

@@ -125,20 +125,35 @@ if __name__ == "__main__":
 
 def test_install_rebinds_reference_names(yb):
     from yolo_from_scratch_b200 import install as inst, ops
+    import torchvision
+    tv_nms = torchvision.ops.batched_nms
     m, _ = fake_train_module()
-    orig_getitem = m.YOLODataset.__getitem__
+    orig_getitem, orig_predict = m.YOLODataset.__getitem__, m.predict
     inst.install(m)
     try:
         assert m.decode_predictions is ops.decode_predictions and m.ciou_loss is ops.ciou_loss
         assert m.yolo_loss is ops.yolo_loss and m.train_epoch() is ops.yolo_loss_multiscale
-        assert m.predict() is ops.batched_nms
+        # predict is rebound as a whole (f-3) with the reference's signature, plus a batched variant;
+        # torchvision is NOT patched process-wide any more
+        import inspect
+        assert m.predict is not orig_predict and callable(m.predict_batch)
+        assert list(inspect.signature(m.predict).parameters) == ["model", "image_path", "device", "num_classes",
+                                                                 "conf_threshold", "iou_threshold"]
+        assert torchvision.ops.batched_nms is tv_nms
         assert m.YOLODataset.__getitem__ is not orig_getitem
         inst.install(m)  # idempotent
     finally:
         inst.uninstall(m)
-    import torchvision
-    assert m.predict() is torchvision.ops.batched_nms and m.predict() is not ops.batched_nms
+    assert m.predict is orig_predict and not hasattr(m, "predict_batch")
     assert m.decode_predictions(None, None) == "ref" and m.YOLODataset.__getitem__ is orig_getitem
+    # the round-1 behaviour is still available: the reference's own predict with torchvision's name rebound
+    m2, _ = fake_train_module()
+    inst.install(m2, patch_torchvision=True, patch_predict=False)
+    try:
+        assert m2.predict() is ops.batched_nms
+    finally:
+        inst.uninstall(m2)
+    assert m2.predict() is tv_nms and torchvision.ops.batched_nms is tv_nms
 
 
 def test_import_hook_and_launcher(yb, tmp_path):
@@ -175,6 +190,8 @@ def test_install_on_live_reference(yb, reference_module):
             b = inspect.signature(getattr(ops, n))
             assert list(a.parameters) == list(b.parameters), n
             assert [p.default for p in a.parameters.values()] == [p.default for p in b.parameters.values()], n
+        a, b = inspect.signature(ref.__yolo_b200_saved__["predict"]), inspect.signature(ref.predict)   # f-3
+        assert str(a) == str(b) and ref.predict is not ref.__yolo_b200_saved__["predict"]
     finally:
         inst.uninstall(ref)
 

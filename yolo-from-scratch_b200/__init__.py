@@ -9,7 +9,7 @@ from . import _lib
 from .ops import (batched_nms, batched_nms_padded, build_targets, ciou_loss, compute_anchor_iou,
                   decode_predictions, default_anchors, detect_batch, detect_batch_nchw, detections_to_lists, heads_from_nchw, eval_counts, eval_epoch,
                   filter_candidates,
-                  loss_forward_backward, nms, nms_retry_overflow, pack_detections,
+                  loss_forward_backward, nms, nms_retry_overflow, pack_detections, predict_heads,
                   NMS_GRAPH, NMS_BITMASK, HotPathGraph, LAYOUT_BHWAC, LAYOUT_NCHW, PackedLabels, pack_labels, pack_labels_host, yolo_loss,
                   yolo_loss_multiscale, yolo_loss_multiscale_labels, yolo_loss_multiscale_nchw)
 
@@ -18,5 +18,5 @@ __all__ = [
     "build_targets", "filter_candidates", "nms", "batched_nms", "batched_nms_padded", "detect_batch",
     "detections_to_lists", "pack_detections", "loss_forward_backward", "yolo_loss_multiscale_labels",
     "PackedLabels", "pack_labels", "pack_labels_host", "eval_counts", "eval_epoch", "yolo_loss_multiscale_nchw",
-    "detect_batch_nchw", "heads_from_nchw", "HotPathGraph", "LAYOUT_BHWAC", "LAYOUT_NCHW", "default_anchors",
+    "detect_batch_nchw", "heads_from_nchw", "predict_heads", "HotPathGraph", "LAYOUT_BHWAC", "LAYOUT_NCHW", "default_anchors",
 ]

@@ -565,10 +565,157 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fallback inside the resolve kernel: an image whose suppression graph does not fit the edge list
+// (heavily clustered boxes: a trained detector at a low confidence threshold, thousands of copies of
+// one box) or whose class ids exceed the sort key is resolved right here, on the device, by the
+// blocked greedy algorithm: ranks are walked in blocks of 512; a block is first tested against every
+// box kept so far, then against itself through a 512x512 bitmask with a serial scan by one warp.
+// Work is M x K pair tests (K = kept boxes), small exactly when the graph is dense.  torchvision's
+// exact fma/div arithmetic with the higher-scored box as `a`; no workspace beyond the caller's
+// keep row.  The host never sees n_keep = -1 from the graph algorithm any more.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGreedyT = 512;
+struct GreedySmem {
+    float4 blk[kGreedyT];        // boxes of the current block of ranks (offset trick applied)
+    float4 kt[kGreedyT];         // a tile of already kept boxes
+    long long bcls[kGreedyT];
+    long long kcls[kGreedyT];
+    u32 mask[kGreedyT * (kGreedyT / 32)];
+    u32 dead[kGreedyT / 32];
+    u32 keptbits[kGreedyT / 32];
+    u32 K;
+};
+
+__device__ __forceinline__ bool iou_gt_exact(const float4 a, const float4 b, const float thr) {
+    // torchvision devIoU (sm_100 SASS): den = fma(bw, bh, Sa) - inter, IEEE division, a = higher score
+    const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+    const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    const float w = fmaxf(right - left, 0.0f), h = fmaxf(bottom - top, 0.0f);
+    const float inter = w * h;
+    const float sa = (a.z - a.x) * (a.w - a.y);
+    const float den = __fmaf_rn(b.z - b.x, b.w - b.y, sa) - inter;
+    return (inter / den) > thr;
+}
+
+__device__ void greedy_resolve(const GArgs& a, const GImg& info, int b, GreedySmem& g) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = tid & (kGreedyT - 1), h = tid / kGreedyT;       // kResolveThreads == 2 * kGreedyT
+    const int M = info.M;
+    const size_t off = (size_t)b * a.cap;
+    const float4* boxes = a.boxes + off;
+    const int64_t* classes = a.classes ? a.classes + off : nullptr;
+    const u32* __restrict__ order = a.order + off;
+    int64_t* keep = a.keep + off;
+    const float thr = a.thr;
+    const bool trick = info.mode == G_TRICK, per_class = info.mode == G_CLASS;
+    const float far = 3.0e38f;
+    constexpr int W = kGreedyT / 32, HALF = kGreedyT / 2;
+    if (tid == 0) g.K = 0u;
+    __syncthreads();
+    for (int r0 = 0; r0 < M; r0 += kGreedyT) {
+        const int n = min(kGreedyT, M - r0);
+        if (tid < kGreedyT) {
+            float4 q = make_float4(far, far, far, far);
+            long long c = 0;
+            if (tid < n) {
+                const u32 idx = order[r0 + tid];
+                q = boxes[idx];
+                if (classes) c = classes[idx];
+                if (trick) {
+                    const float o = (float)c * info.s_off;
+                    q.x += o; q.y += o; q.z += o; q.w += o;
+                }
+            }
+            g.blk[tid] = q;
+            g.bcls[tid] = c;
+        }
+        if (tid < W) {
+            const int rem = n - tid * 32;
+            g.dead[tid] = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : ~((1u << rem) - 1u));
+        }
+        __syncthreads();
+        const float4 q = g.blk[i];
+        const long long qc = g.bcls[i];
+        bool dead = i >= n;
+        // phase 1: against everything kept so far (each half of the CTA takes half of every tile)
+        const int K = (int)g.K;
+        for (int k0 = 0; k0 < K; k0 += kGreedyT) {
+            const int nk = min(kGreedyT, K - k0);
+            if (tid < nk) {
+                const int64_t kidx = keep[k0 + tid];
+                float4 kq = boxes[kidx];
+                long long c = 0;
+                if (classes) c = classes[kidx];
+                if (trick) {
+                    const float o = (float)c * info.s_off;
+                    kq.x += o; kq.y += o; kq.z += o; kq.w += o;
+                }
+                g.kt[tid] = kq;
+                g.kcls[tid] = c;
+            }
+            __syncthreads();
+            if (!dead) {
+                const int j1 = min(nk, h * HALF + HALF);
+                for (int j = h * HALF; j < j1; ++j) {
+                    if ((!per_class || g.kcls[j] == qc) && iou_gt_exact(g.kt[j], q, thr)) { dead = true; break; }
+                }
+            }
+            __syncthreads();
+        }
+        if (dead && i < n) atomicOr(&g.dead[i >> 5], 1u << (i & 31));
+        __syncthreads();
+        dead = (g.dead[i >> 5] >> (i & 31)) & 1u;
+        // phase 2: row i of the block's bitmask, columns j > i (this half's 8 words)
+#pragma unroll 1
+        for (int w = 0; w < W / 2; ++w) {
+            const int wi = h * (W / 2) + w;
+            u32 word = 0u;
+            if (!dead && wi * 32 + 31 > i) {
+                for (int bit = 0; bit < 32; ++bit) {
+                    const int j = wi * 32 + bit;
+                    if (j > i && j < n && (!per_class || g.bcls[j] == qc) && iou_gt_exact(q, g.blk[j], thr)) word |= 1u << bit;
+                }
+            }
+            g.mask[i * W + wi] = word;
+        }
+        __syncthreads();
+        if (warp == 0) {  // serial scan in rank order; lanes < W hold the removed words
+            u32 rem = lane < W ? g.dead[lane] : 0xffffffffu;
+            u32 kb = 0u;
+            for (int r = 0; r < n; ++r) {
+                const u32 rw = __shfl_sync(0xffffffffu, rem, r >> 5);
+                if (!((rw >> (r & 31)) & 1u)) {
+                    if (lane == (r >> 5)) kb |= 1u << (r & 31);
+                    if (lane < W) rem |= g.mask[r * W + lane];
+                }
+            }
+            if (lane < W) g.keptbits[lane] = kb;
+        }
+        __syncthreads();
+        u32 total = 0, before = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const u32 c = __popc(g.keptbits[w]);
+            if (w < (i >> 5)) before += c;
+            total += c;
+        }
+        if (tid < n) {
+            const u32 bits = g.keptbits[tid >> 5];
+            if ((bits >> (tid & 31)) & 1u)
+                keep[g.K + before + __popc(bits & ((1u << (tid & 31)) - 1u))] = (int64_t)order[r0 + tid];
+        }
+        __syncthreads();
+        if (tid == 0) g.K += total;
+        __syncthreads();
+    }
+    if (tid == 0) a.n_keep[b] = (int)g.K;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fixed-point resolve + emit
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GArgs a) {
-    extern __shared__ u32 s_bits[];  // U | K | fK | fU, each nw words
+    extern __shared__ __align__(16) u32 s_bits[];  // U | K | fK | fU, each nw words (or a GreedySmem)
     __shared__ u32 s_scan[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const GImg info = a.info[b];
@@ -578,7 +725,7 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
         return;
     }
     if (info.overflow || (u64)info.n_edges > a.edges_per_img) {
-        if (tid == 0) a.n_keep[b] = -1;
+        greedy_resolve(a, info, b, *reinterpret_cast<GreedySmem*>(s_bits));
         return;
     }
     const int nw = (M + 31) >> 5;
@@ -719,10 +866,11 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     YB_LAUNCH("graph_gather_kernel", st, graph_gather_kernel<<<ggrid, kGatherThreads, 0, st>>>(a));
     const int ctas = sm_count() * 4;  // 4 resident CTAs per SM (launch bounds)
     YB_LAUNCH("graph_edge_kernel", st, graph_edge_kernel<<<ctas, kEdgeThreads, 0, st>>>(a));
-    const size_t dyn = (size_t)((cap + 31) / 32) * 4 * 4;
+    static_assert(kResolveThreads == 2 * kGreedyT, "greedy_resolve splits the CTA in two halves");
+    size_t dyn = (size_t)((cap + 31) / 32) * 4 * 4;
+    if (dyn < sizeof(GreedySmem)) dyn = sizeof(GreedySmem);
     YB_CHECK_ARG(dyn <= 200 * 1024, "nms(graph): cap too large for the resolve kernel");
-    if (dyn > 40 * 1024)
-        YB_CUDA(cudaFuncSetAttribute(graph_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    YB_CUDA(cudaFuncSetAttribute(graph_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     YB_LAUNCH("graph_resolve_kernel", st, graph_resolve_kernel<<<B, kResolveThreads, dyn, st>>>(a));
     return 0;
 }

@@ -17,7 +17,13 @@ __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ bo
         s_base = base;
         if (blockIdx.x == 0) {
             offsets[b] = base;
-            if (b == B - 1) offsets[B] = base + max(n_keep[b], 0);
+            if (b == B - 1) {
+                // an image NMS gave up on (n_keep < 0: the bitmask algorithm with too small a workspace) must not
+                // read as "no detections": the total becomes -1 and the host raises at its synchronisation point
+                bool failed = false;
+                for (int i = 0; i < B; ++i) failed |= n_keep[i] < 0;
+                offsets[B] = failed ? -1 : base + max(n_keep[b], 0);
+            }
         }
     }
     __syncthreads();

@@ -2,11 +2,12 @@
 
 The reference (`train.py`) has no plugin API; its callers resolve `decode_predictions`,
 `ciou_loss`, `yolo_loss`, `yolo_loss_multiscale` through module globals at call time
-(train.py:796, :818, :874, :909, :987, :993, :1154), the CLI resolves `eval_epoch` the same way
-(:1413, :1436, :1523), `predict` imports
-`torchvision.ops.batched_nms` at call time (:1232), and target assignment lives in
+(train.py:796, :818, :874, :909, :987, :993, :1154), the CLI resolves `eval_epoch` and `predict` the same way
+(:1413, :1436, :1523; :1444, eval.py:8 via `from train import predict`), and target assignment lives in
 `YOLODataset.__getitem__` / `compute_anchor_iou` (:108-131, :147-205).  `install(train_module)`
-rebinds exactly those names; the file on disk is untouched.
+rebinds exactly those names; the file on disk is untouched.  `predict` is rebound as a whole
+(SURVEY 8f-3), so the swap no longer touches `torchvision.ops.batched_nms` for the rest of the process
+(`patch_torchvision=True` restores the round-1 behaviour for callers that use the reference's own predict).
 
   import train; from yolo_from_scratch_b200.install import install; install(train)
   pytest -p yolo_from_scratch_b200.pytest_plugin /path/to/reference/tests     # unchanged suite
@@ -32,6 +33,11 @@ def _make_getitem(train_module):
     def __getitem__(self, idx):
         import numpy as np
         import torch
+        if _in_dataloader_worker():
+            raise RuntimeError(
+                "YOLODataset.__getitem__ on the B200 path runs its label loop on the GPU and cannot be used from "
+                "DataLoader worker processes (CUDA after fork); use num_workers=0 like the reference (train.py:1471-1474) "
+                "or install(..., patch_dataset=False) to keep the reference's CPU label loop")
         g = train_module.__dict__
         pil_img = g["Image"].open(self.imgs[idx]).convert("RGB")                      # :135
         orig_w, orig_h = pil_img.size
@@ -52,9 +58,53 @@ def _make_getitem(train_module):
     return __getitem__
 
 
-def install(train_module, patch_torchvision=True, patch_dataset=True, patch_eval=True):
+def _make_predict(train_module):
+    """Signature-identical replacements for predict() (train.py:1114-1250) plus a batched variant.  Image
+    loading and letterbox stay the reference's (host image I/O is out of scope); the model call is the
+    caller's model; everything after it (:1140-1246) is ops.predict_heads."""
+    def _load(image_path, img_size, device):
+        import numpy as np
+        import torch
+        g = train_module.__dict__
+        pil_img = g["Image"].open(image_path).convert("RGB")                                   # :1134
+        pil_img, scale, pad_top, pad_left = g["letterbox_resize"](pil_img, img_size)           # :1137
+        img = torch.from_numpy(np.array(pil_img)).permute(2, 0, 1).float() / 255.0             # :1138
+        return img, (scale, pad_top, pad_left)
+
+    def predict(model, image_path, device, num_classes=1, conf_threshold=0.5, iou_threshold=0.4):
+        return predict_batch(model, [image_path], device, num_classes, conf_threshold, iou_threshold)[0]
+
+    def predict_batch(model, image_paths, device, num_classes=1, conf_threshold=0.5, iou_threshold=0.4):
+        """predict() for a list of images with ONE model call and one pass of the detection path; returns
+        a list (per image) of the reference's detection lists."""
+        import torch
+        model.eval()                                                                            # :1131
+        img_size = model.img_size
+        if len(image_paths) == 0:
+            return []
+        loaded = [_load(p, img_size, device) for p in image_paths]
+        imgs = torch.stack([im for im, _ in loaded]).to(device)                                 # :1139
+        with torch.no_grad():
+            preds = model(imgs)                                                                 # :1141-1142
+        return ops.predict_heads(preds, model.anchors, img_size, num_classes, conf_threshold, iou_threshold,
+                                 letterbox=[lb for _, lb in loaded])
+    predict.__doc__ = "Drop-in for train.predict (train.py:1114-1250): same arguments, same return value."
+    return predict, predict_batch
+
+
+def _in_dataloader_worker():
+    try:
+        import torch.utils.data
+        return torch.utils.data.get_worker_info() is not None
+    except Exception:  # pragma: no cover
+        return False
+
+
+def install(train_module, patch_torchvision=False, patch_dataset=True, patch_eval=True, patch_predict=True):
     """Rebind the hot-path names of an imported reference `train` module.  Idempotent.
-    patch_eval also swaps `eval_epoch` (its per-anchor python loop becomes one kernel)."""
+    patch_eval also swaps `eval_epoch` (SURVEY 8f-1: its per-anchor python loop becomes one kernel);
+    patch_predict swaps `predict` and adds `predict_batch`; patch_torchvision additionally
+    rebinds torchvision.ops.batched_nms process-wide (off by default: predict no longer needs it)."""
     if getattr(train_module, _MARK, False):
         return train_module
     saved = {}
@@ -64,6 +114,9 @@ def install(train_module, patch_torchvision=True, patch_dataset=True, patch_eval
     if patch_eval and hasattr(train_module, "eval_epoch"):
         saved["eval_epoch"] = train_module.eval_epoch
         train_module.eval_epoch = ops.eval_epoch
+    if patch_predict and hasattr(train_module, "predict"):
+        saved["predict"] = train_module.predict
+        train_module.predict, train_module.predict_batch = _make_predict(train_module)
     if patch_dataset and hasattr(train_module, "YOLODataset"):
         cls = train_module.YOLODataset
         saved["YOLODataset.__getitem__"] = cls.__getitem__
@@ -89,6 +142,10 @@ def uninstall(train_module):
         setattr(train_module, name, saved[name])
     if "eval_epoch" in saved:
         train_module.eval_epoch = saved["eval_epoch"]
+    if "predict" in saved:
+        train_module.predict = saved["predict"]
+        if hasattr(train_module, "predict_batch"):
+            del train_module.predict_batch
     if "YOLODataset.__getitem__" in saved:
         train_module.YOLODataset.__getitem__ = saved["YOLODataset.__getitem__"]
         train_module.YOLODataset.compute_anchor_iou = saved["YOLODataset.compute_anchor_iou"]

@@ -320,7 +320,7 @@ class _YoloLossFn(torch.autograd.Function):
         none = (None,) * 4
         if not any(want):
             return none + (None,) * (3 * S)
-        if g_bbox is None and g_obj is None and g_cls is None:
+        if g_bbox is None and g_obj is None and g_cls is None and ctx.fused_grads is not None:
             grads = ctx.fused_grads
             if g_total is None:
                 grads = [None if g is None else torch.zeros_like(g) for g in grads]
@@ -332,6 +332,8 @@ class _YoloLossFn(torch.autograd.Function):
                         _lib.check(L.yb_scale_inplace(g.data_ptr(), g.numel(), f.data_ptr(), _stream()),
                                    "yb_scale_inplace")
         else:
+            # gradients on bbox/obj/cls as well, or a second backward through the same graph (retain_graph=True:
+            # the fused buffers were handed out, and possibly scaled in place, by the first one): recompute
             tensors = ctx.saved_tensors
             preds, tgts, ancs = tensors[:S], tensors[S:2 * S], tensors[2 * S:3 * S]
             z = lambda g: 0.0 if g is None else float(g)
@@ -425,30 +427,43 @@ def pack_labels(labels: Sequence, img_size: int, letterbox: Optional[Sequence] =
 
 
 def yolo_loss_multiscale_labels(predictions, labels, anchors_list, num_classes=1, img_size=640, letterbox=None,
-                                group=None):
+                                group=None, check=False):
     """yolo_loss_multiscale (train.py:840-886) fed by LABEL LISTS instead of dense targets: the
     assignment of YOLODataset.__getitem__ (:147-205) runs on the device and reaches the loss in
     sparse form.  `labels`: per-image (n_i,5) arrays, or a PackedLabels already on the device.
-    Returns the same (total, sum bbox, sum obj, sum cls) as the dense call on the reference's targets."""
+    Returns the same (total, sum bbox, sum obj, sum cls) as the dense call on the reference's targets.
+
+    A label that maps outside the grid or the class range makes the reference (and `build_targets`) raise
+    IndexError (train.py:193-205); here it is dropped on the device and recorded in `PackedLabels.status`.
+    `check=True` reads that flag right after the call (one host synchronisation) and raises like the
+    reference; asynchronous callers (CUDA graphs, pipelined loops) must call `PackedLabels.check()` at their
+    own synchronisation point instead."""
     S = min(len(predictions), len(anchors_list), len(MULTISCALE_OBJ_WEIGHTS))
     packed = labels if isinstance(labels, PackedLabels) else pack_labels(labels, img_size, letterbox)
-    return _loss_common(list(predictions[:S]), [None] * S, list(anchors_list[:S]), num_classes,
-                        MULTISCALE_OBJ_WEIGHTS[:S], group=group, sparse=packed)
+    out = _loss_common(list(predictions[:S]), [None] * S, list(anchors_list[:S]), num_classes,
+                       MULTISCALE_OBJ_WEIGHTS[:S], group=group, sparse=packed)
+    if check:
+        packed.check()
+    return out
 
 
 def yolo_loss_multiscale_nchw(raw_heads, targets, anchors_list, num_classes=1, img_size=640, letterbox=None,
-                              group=None):
+                              group=None, check=False):
     """yolo_loss_multiscale on the head convs' OWN outputs (B, A*(5+nc), H, W) — SURVEY 8f-2: the
     view/permute/contiguous of train.py:608-609 (a full read+write of every head, plus its backward)
     is not needed; the gradient comes back in the same NCHW layout, ready for the conv backward.
     `targets`: the reference's dense targets [(B,G,G,A,5+nc)], or label lists / PackedLabels (then
     the assignment runs on the device, as in yolo_loss_multiscale_labels)."""
     S = min(len(raw_heads), len(anchors_list), len(MULTISCALE_OBJ_WEIGHTS))
-    dense = len(targets) > 0 and isinstance(targets[0], torch.Tensor) and targets[0].dim() == 5
-    if isinstance(targets, PackedLabels) or not dense:
-        packed = targets if isinstance(targets, PackedLabels) else pack_labels(targets, img_size, letterbox)
-        return _loss_common(list(raw_heads[:S]), [None] * S, list(anchors_list[:S]), num_classes,
-                            MULTISCALE_OBJ_WEIGHTS[:S], group=group, sparse=packed, layout=LAYOUT_NCHW)
+    is_packed = isinstance(targets, PackedLabels)
+    dense = (not is_packed) and len(targets) > 0 and isinstance(targets[0], torch.Tensor) and targets[0].dim() == 5
+    if not dense:
+        packed = targets if is_packed else pack_labels(targets, img_size, letterbox)
+        out = _loss_common(list(raw_heads[:S]), [None] * S, list(anchors_list[:S]), num_classes,
+                           MULTISCALE_OBJ_WEIGHTS[:S], group=group, sparse=packed, layout=LAYOUT_NCHW)
+        if check:
+            packed.check()   # see yolo_loss_multiscale_labels
+        return out
     S = min(S, len(targets))
     return _loss_common(list(raw_heads[:S]), list(targets[:S]), list(anchors_list[:S]), num_classes,
                         MULTISCALE_OBJ_WEIGHTS[:S], group=group, layout=LAYOUT_NCHW)
@@ -644,9 +659,10 @@ def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_
                        algo=NMS_GRAPH, return_workspace=False):
     """NMS for B images at once.  boxes (B,cap,4), scores (B,cap), classes (B,cap) int64 or None,
     counts (B,) int32 or None.  Returns (keep (B,cap) int64, n_keep (B,) int32) on the GPU, nothing
-    synchronised.  With the default sparse-graph algorithm an image whose suppression graph does
-    not fit the workspace reports n_keep = -1; `nms_retry_overflow` re-runs those on the dense
-    bitmask algorithm (detections_to_lists / batched_nms do that for you)."""
+    synchronised.  The default sparse-graph algorithm resolves an image whose suppression graph does
+    not fit the workspace on the device, in the same launch (blocked greedy pass), so n_keep is never
+    negative; only the dense bitmask algorithm with an undersized workspace can report n_keep = -1,
+    which `pack_detections` turns into a total of -1 and `detections_to_lists` into an exception."""
     dev = boxes.device
     B, cap = boxes.shape[0], boxes.shape[1]
     L = _lib.lib()
@@ -773,13 +789,27 @@ def pack_detections(det):
 def detections_to_lists(det):
     """[(x1, y1, x2, y2, conf, class_id), ...] per image (train.py:1242-1246): one pack kernel and
     two D2H copies instead of K*6 `.item()` syncs."""
-    if bool((det["n_keep"] < 0).any()):  # graph algorithm overflowed for some image: dense re-run
-        nms_retry_overflow(det["boxes"], det["scores"], det["classes"], det["counts"], det["iou_threshold"],
-                           det["trick_max_numel"], det["keep"], det["n_keep"])
     rows, offsets = pack_detections(det)
     off = offsets.cpu().tolist()
+    if off[-1] < 0:
+        raise RuntimeError("NMS failed for an image (n_keep < 0: bitmask algorithm with too small a workspace)")
     host = rows[:off[-1]].cpu().tolist()
     return [[(r[0], r[1], r[2], r[3], r[4], int(r[5])) for r in host[off[b]:off[b + 1]]] for b in range(len(off) - 1)]
+
+
+def predict_heads(preds, anchors_list, img_size, num_classes=1, conf_threshold=0.5, iou_threshold=0.4, letterbox=None):
+    """Everything predict() does after the model call (train.py:1140-1246), for a batch of B images: decode,
+    objectness filter, class max, pixel xyxy, letterbox reverse, global NMS, detection list.  preds are the
+    model's heads [(B,G,G,A,5+nc)], letterbox per image (scale, pad_top, pad_left) as returned by the
+    reference's letterbox_resize.  Returns, per image, [(x1, y1, x2, y2, conf, class_id), ...] in original
+    image coordinates, descending score — the reference's return value, one host synchronisation per batch
+    instead of a `nonzero` per scale (:1170) and K x 6 `.item()` calls (:1242-1246) per image."""
+    # torchvision picks batched_nms' algorithm from the device its inputs live on (boxes.py:80); in
+    # predict() that is the device the model ran on
+    on_cpu = preds[0].device.type == "cpu"
+    det = detect_batch(list(preds), anchors_list, img_size, num_classes, conf_threshold, iou_threshold, letterbox=letterbox,
+                       trick_max_numel=TRICK_MAX_NUMEL_CPU if on_cpu else TRICK_MAX_NUMEL_CUDA)
+    return detections_to_lists(det)
 
 
 # --------------------------------------------------------------------------------------------
@@ -796,7 +826,7 @@ class HotPathGraph:
       targets[s] dense (B,G,G,A,5+nc) (targets="dense": the reference's call signature)
     Static outputs: losses (4,) [total, bbox, obj, cls], grads[s] (gradient of `total`), det (the
     detect_batch dict), rows (B*cap,6) + offsets (B+1,) from pack_detections.
-    Images whose NMS graph overflowed report det["n_keep"] < 0, as with detect_batch."""
+    An image whose NMS graph overflows the edge list is resolved exactly inside the same launch."""
 
     def __init__(self, batch, img_size, num_classes, anchors_list, conf_threshold=0.5, iou_threshold=0.4, max_gt=50,
                  targets="labels", layout=LAYOUT_BHWAC, num_anchors=3, device=None, adopt_heads=None,
