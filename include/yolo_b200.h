@@ -226,9 +226,10 @@ int yb_batched_nms(const float* boxes, const float* scores, const int64_t* class
                    void* ws, size_t ws_bytes, void* stream);
 
 /* Statistics of the last YB_NMS_GRAPH call that used workspace `ws` (bench/tests; synchronises the
- * stream): IoU pair tests executed and edges found, summed over the B images.  Outputs are HOST pointers (nullable). */
+ * stream), summed over the B images: IoU pair tests executed by the half-precision filter, edges found, and
+ * pairs that passed the filter and were decided exactly in fp32.  Outputs are HOST pointers (nullable). */
 int yb_nms_graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned long long* evals_host,
-                       unsigned long long* edges_host, void* stream);
+                       unsigned long long* edges_host, unsigned long long* cands_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * detection list of predict()                                              train.py:1236-1246

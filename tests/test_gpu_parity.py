@@ -812,9 +812,9 @@ def test_nms_greedy_fallback_is_exact(yb, monkeypatch, mode, n_cls):
 
 def ctypes_stats(yb, ws, B, cap):
     import ctypes
-    ev, ed = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    ev, ed, ca = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
     yb._lib.check(yb._lib.lib().yb_nms_graph_stats(ws.data_ptr(), ws.numel(), B, cap, ctypes.byref(ev), ctypes.byref(ed),
-                                                   torch.cuda.current_stream().cuda_stream), "stats")
+                                                   ctypes.byref(ca), torch.cuda.current_stream().cuda_stream), "stats")
     return int(ev.value), int(ed.value)
 
 

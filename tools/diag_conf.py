@@ -9,7 +9,7 @@ lib = yb._lib.lib()
 dev = torch.device("cuda")
 anchors = ops.default_anchors(dev)
 import itertools
-sets = [[h.to(dev) for h in bench.make_heads(64, 640, 1, 1234 + 1000 * k)] for k in range(4)]
+sets = [[h.to(dev) for h in bench.make_heads(64, 640, 1, 1234 + 1000 * k)] for k in range(1)]
 for heads, conf in itertools.product(sets, [float(x) for x in sys.argv[1:]] or [0.5, 0.25, 0.001]):
     for _ in range(3):
         det = ops.detect_batch(heads, anchors, 640, 1, conf, 0.4)
@@ -23,7 +23,7 @@ for heads, conf in itertools.product(sets, [float(x) for x in sys.argv[1:]] or [
     lib.yb_timing_collect(buf, len(buf))
     st = ops.nms_graph_stats(det)
     print("conf", conf, "cand/img", float(det["counts"].float().mean()), "max", int(det["counts"].max()), "kept/img", float(det["n_keep"].float().mean()),
-          "evals", st[0], "edges", st[1], "edges/img max?", st[1] / 64)
+          "evals", st[0], "edges", st[1], "cands", st[2], "cands/edge", st[2] / max(st[1], 1))
     for ln in buf.value.decode().strip().splitlines():
         n, c, t = ln.split()
         print("   %-28s %8.1f us" % (n, float(t) / int(c) * 1e3))

@@ -551,11 +551,11 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
 
 namespace yb {
 int graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned long long* evals, unsigned long long* edges,
-                cudaStream_t st);
+                unsigned long long* cands, cudaStream_t st);
 }
 extern "C" int yb_nms_graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned long long* evals_host,
-                                  unsigned long long* edges_host, void* stream) {
-    return yb::graph_stats(ws, ws_bytes, B, cap, evals_host, edges_host, (cudaStream_t)stream);
+                                  unsigned long long* edges_host, unsigned long long* cands_host, void* stream) {
+    return yb::graph_stats(ws, ws_bytes, B, cap, evals_host, edges_host, cands_host, (cudaStream_t)stream);
 }
 
 extern "C" size_t yb_nms_graph_workspace_bytes(int B, int cap, int edges_per_box) {

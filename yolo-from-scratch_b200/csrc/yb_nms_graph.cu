@@ -28,6 +28,7 @@
 // Bound: fp32 SIMT issue on the pair evaluations that survive culling.
 #include "yb_common.cuh"
 #include "yb_sort.cuh"
+#include <cuda_fp16.h>
 #include <vector>
 
 namespace yb {
@@ -48,7 +49,8 @@ struct GImg {
     int n_tiles;
     u32 n_edges;
     float s_off, t2;  // coordinate offset step; pruning threshold thr*(1-2^-10) (or -1: no pruning)
-    unsigned long long n_evals;  // statistics: (row, sub-tile) items evaluated (kSub pair tests each)
+    unsigned long long n_evals;  // statistics: (row, sub-tile) items filtered (kSub pair tests each)
+    unsigned long long n_cands;  // statistics: pairs that passed the half-precision filter (decided exactly in fp32)
 };
 
 struct GArgs {
@@ -59,6 +61,9 @@ struct GArgs {
     int B, cap, tcap;
     float thr;
     int thr_fast_ok;
+    float t3;       // thr * (1 - 2^-6): threshold of the half-precision culling tests
+    u32 k16x2;      // half2 {K, K}, K = (1+th)/th * (1+2^-6) rounded up, th = thr * (1 - 2^-12)
+    int hexp;       // local frames map a row tile's half extent to [2^hexp, 2^(hexp+1))
     long long trick_max_numel;
     u32 *k0, *v0, *k1, *v1, *k2, *v2;  // (B,cap) radix ping-pong buffers
     u32* order;                        // (B,cap) score rank -> original index      (score CTA)
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(NT) graph_sort_kernel(const GArgs a) {
     if (b == 0 && blockIdx.y == 0 && tid == 0) *a.ticket = 0u;
     if (M == 0) {
         if (tid == 0 && blockIdx.y == 1) {
-            GImg z = {0, G_PLAIN, 0, 0, 0, 0u, 0.0f, -1.0f, 0ull};
+            GImg z = {0, G_PLAIN, 0, 0, 0, 0u, 0.0f, -1.0f, 0ull, 0ull};
             *info = z;
         }
         return;
@@ -216,10 +221,13 @@ __global__ void __launch_bounds__(NT) graph_sort_kernel(const GArgs a) {
     if (tid == 0) {
         GImg o;
         o.M = M; o.mode = mode; o.exact = exact ? 1 : 0;
-        o.overflow = (bad & 2) ? 2 : 0;
+        // 2: class ids beyond the sort key; 4: boxes or threshold the half-precision filter cannot serve (NaN/Inf,
+        // inverted, |coordinate| > 1e17, thr outside [0.03, 1e30]).  Both are decided by the resolve kernel's greedy pass.
+        o.overflow = ((bad & 2) ? 2 : 0) | (exact ? 4 : 0);
         o.n_tiles = (M + kTile - 1) / kTile; o.n_edges = 0u; o.s_off = s_off;
         o.t2 = exact ? -1.0f : a.thr * (1.0f - 9.765625e-4f);
         o.n_evals = 0ull;
+        o.n_cands = 0ull;
         *info = o;
     }
 }
@@ -280,29 +288,78 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
 }
 
 // ------------------------------------------------------------------------------------------------
-// edge discovery
+// edge discovery (v4: packed fp16 candidate filter + exact fp32 decision)
+//
+// 99.4 % of the pair tests that survive the tile statistics find no edge (103 tests, 0.66 edges per box on
+// the bench workload), and the kernel is bound by the ALU/FMA issue rate (FMNMX, HMNMX2, HFMA2: 2 warp
+// instructions per clock and SM, profiles/r2_ubench_pipes.txt).  So the bulk of the tests runs as a
+// CONSERVATIVE filter on packed halves — one HMNMX2/HADD2/HFMA2 handles two columns — in a coordinate frame
+// local to the row tile (origin = centre of the tile's bounding box, power-of-two scale that maps its half
+// extent to [2^h, 2^(h+1))).  Every conversion is rounded in the direction that can only ADD candidates
+// (lower corners down, upper corners up, areas towards zero, thresholds with 2^-6 of slack), boxes too small
+// for the half format in that frame are made unconditional candidates, and whatever passes is queued and
+// decided 32 at a time in fp32 with torchvision's arithmetic (division-free margin test, exact fma/div when
+// ambiguous).  The edge set is therefore exactly the set of pairs with IoU > thr; only the amount of work
+// depends on the half-precision stage.  Images the filter cannot serve (NaN/Inf/inverted boxes, thresholds
+// outside [0.03, 1e30]) are not handled here at all: the resolve kernel's greedy pass decides them.
 // ------------------------------------------------------------------------------------------------
-struct RowAux { u32 rank; u32 cls; };
-
-// Per-warp shared memory of the edge kernel.
-struct RowRec {  // 32 bytes: one address computation serves the box, its area and (rarely) rank/class
+struct RowF {  // 32 bytes: the fp32 row of the exact stage
     float4 box;
     float area;
     u32 rank, cls, pad;
 };
-constexpr int kQueue = kTile + 8;  // sub-tiles queued per level-2 step (<= 32) + < 4 left over
-struct EdgeWarp {
-    RowRec row[kTile + 1];  // rows of tile I; row[kTile] is a sentinel that overlaps nothing (pads the item list)
-    float4 col[kTile];      // columns of the current chunk: 4 surviving sub-tiles x 8 boxes
-    float carea[kTile];
-    RowAux caux[kTile];     // score rank and class of the chunk's columns
-    u32 tl[kTile];          // compaction scratch: surviving tiles of the current step
-    u32 sub[kQueue];        // queue of surviving sub-tile ids (J*kSubs+s) ...
-    float4 sbx[kQueue];     // ... with their bounding boxes ...
-    float2 sar[kQueue];     // ... and area ranges (kept from the level-2 test: no second global read)
-    unsigned short item[kTile * kSubs + kSubs];  // (slot << 11) | (row * 32): packed work list of a chunk
-    uint2 ebuf[2 * kTile];  // edges found, flushed to the image's list 33..64 at a time (one atomic per flush)
+struct Rec16 {   // 32 bytes: a box (rows: the same box in both halves; columns: two neighbouring columns) in the
+    uint4 box;   // row tile's local frame: half2 x1 | y1 | x2 | y2, corners rounded outwards
+    u32 area;    // half2 area, rounded towards zero, capped at 32768; -60000 = "too small for the format"
+    u32 pad[3];
 };
+constexpr int kSlots = 8;            // sub-tiles per chunk: 64 columns, two per lane
+constexpr int kQueue = kTile + 8;    // sub-tiles queued per level-2 step (<= 32) + < 8 left over
+constexpr int kCand = 3 * kTile;     // candidate queue: processed when >= 32, one iteration adds <= 64
+struct EdgeWarp {
+    RowF rowf[kTile];
+    Rec16 row16[kTile + 1];          // [kTile]: a sentinel that overlaps nothing (pads the item list)
+    Rec16 col16[kSlots * 4];         // lane l of the chunk: columns 2*(l&3), +1 of slot l>>2
+    u32 tl[kTile];                   // compaction scratch: surviving tiles of the current step
+    u32 sub[kQueue];                 // queue of surviving sub-tile ids (J*kSubs+s) ...
+    uint2 sbx[kQueue];               // ... their bounding boxes in the local frame: half2 {x1,y1} down | {x2,y2} up ...
+    u32 sar[kQueue];                 // ... and half2 {max area up, -(t3 * min area) down}
+    u32 item[kSlots * kTile + kSlots];  // (slot * 128) << 16 | (row * 32): byte offsets of the item's column / row records
+    u32 cand[kCand];                 // (row << 24) | column position: pairs that passed the half-precision filter
+    uint2 ebuf[2 * kTile];           // edges found, flushed to the image's list 33..64 at a time
+};
+
+__device__ __forceinline__ u32 pack_h2(const __half lo, const __half hi) {
+    return (u32)__half_as_ushort(lo) | ((u32)__half_as_ushort(hi) << 16);
+}
+__device__ __forceinline__ __half2 as_h2(const u32 v) { return *reinterpret_cast<const __half2*>(&v); }
+__device__ __forceinline__ u32 as_u32(const __half2 v) { return *reinterpret_cast<const u32*>(&v); }
+// both halves of a >= the halves of b (ordered: false on NaN): one HSETP2
+__device__ __forceinline__ bool h2_all_ge(const u32 a, const u32 b) {
+    u32 r;
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ge.f16x2 p|q, %1, %2;\n\tand.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"(a), "r"(b));
+    return r != 0u;
+}
+// either half of a >= 0 (ordered): bit 0 = low half, bit 1 = high half
+__device__ __forceinline__ u32 h2_ge0_bits(const u32 a) {
+    u32 r;
+    asm("{\n\t.reg .pred p, q;\n\t.reg .u32 t;\n\tsetp.ge.f16x2 p|q, %1, %2;\n\tselp.u32 %0, 1, 0, p;\n\tselp.u32 t, 2, 0, q;\n\tor.b32 %0, %0, t;\n\t}"
+        : "=r"(r) : "r"(a), "r"(0u));
+    return r;
+}
+
+struct Frame {   // local frame of a row tile
+    float S, S2, nox, noy;   // scale (power of two), its square, -origin*S
+};
+// area of a nice box in the local frame: lower bound (towards zero), capped, tiny -> always-candidate marker
+__device__ __forceinline__ __half area16_down(const float4 q, const Frame& f) {
+    const float a = __fmul_rd(__fmul_rd(__fsub_rd(q.z, q.x), __fsub_rd(q.w, q.y)), f.S2);
+    if (!(a >= 2.44140625e-4f)) return __float2half_rz(-60000.0f);   // < 2^-12: products would leave the normal range
+    return __float2half_rz(fminf(a, 32768.0f));
+}
+__device__ __forceinline__ float area_up(const float4 q, const Frame& f) {
+    return __fmul_ru(__fmul_ru(__fsub_ru(q.z, q.x), __fsub_ru(q.w, q.y)), f.S2);
+}
 
 // Append the warp's buffered edges to image b's list.
 __device__ __forceinline__ void edge_flush(const GArgs& a, EdgeWarp& w, int b, uint2* __restrict__ edges, int& n_buf) {
@@ -320,121 +377,158 @@ __device__ __forceinline__ void edge_flush(const GArgs& a, EdgeWarp& w, int b, u
     n_buf = 0;
 }
 
-// One chunk = up to 4 sub-tiles (8 columns each) that survived the tile-level tests against row
-// tile I.  Lane l holds column (l&7) of slot (l>>3).  Rows are culled against each slot's
-// statistics, the surviving (row, slot) items are packed, and every iteration of the pair loop
-// evaluates 4 items x 8 columns: all 32 lanes busy whatever the culling pattern.
-__device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I, int head,
-                                           const float4* __restrict__ sb, const u32* __restrict__ srank,
-                                           const u32* __restrict__ scls,
-                                           uint2* __restrict__ edges, const float4 rq, const bool rvalid,
-                                           const float rw_t, const float rh_t, const float rS, const float rS_t,
-                                           u32& n_evals, int& n_buf) {
+// Exact stage: the queued (row, column) pairs, one per lane.  torchvision's predicate with the division-free
+// margin test; ambiguous lanes redo the exact fma/div arithmetic with the higher-scored box as `a`.
+__device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I,
+                                             const float4* __restrict__ sb, const u32* __restrict__ srank,
+                                             const u32* __restrict__ scls, uint2* __restrict__ edges, int& n_cand,
+                                             int& n_buf) {
     const int lane = threadIdx.x & 31;
-    const int grp = lane / kSub;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float kEps = 9.5367431640625e-07f;     // 2^-20
     const float kTiny = 7.888609052210118e-31f;  // 2^-100
-    const float far = 3.0e38f;
-    const int M = info.M;
-    const bool prune = info.t2 >= 0.0f;
-    const float t2 = info.t2;
+    const float thr = a.thr;
     const bool class_mode = info.mode == G_CLASS;
-    const bool all_exact = info.exact != 0;
+    __syncwarp();
+    for (int k0 = 0; k0 < n_cand; k0 += 32) {
+        const int k = k0 + lane;
+        bool fin = false;
+        u32 rlo = 0u, rhi = 0u;
+        if (k < n_cand) {
+            const u32 e = w.cand[k];
+            const int i = (int)(e >> 24);
+            const int qp = (int)(e & 0xffffffu);
+            const RowF rr = w.rowf[i];
+            const float4 r = rr.box;
+            const float4 q = sb[qp];
+            const u32 crank = srank[qp];
+            const float qw = q.z - q.x, qh = q.w - q.y;
+            const float qarea = qw * qh;
+            const float left = fmaxf(r.x, q.x), right = fminf(r.z, q.z);
+            const float top = fmaxf(r.y, q.y), bottom = fminf(r.w, q.w);
+            const float iw = fmaxf(right - left, 0.0f), ih = fmaxf(bottom - top, 0.0f);
+            const float inter = iw * ih;
+            // den within a few ulp of torchvision's fma form whichever box plays `a`: inside the margin
+            const float den0 = (qarea + rr.area) - inter;
+            const float tt = thr * den0;
+            const float d = inter - tt;
+            bool pr = d > 0.0f;
+            if (!(fabsf(d) > __fmaf_rn(tt, kEps, kTiny))) {
+                const bool row_a = rr.rank < crank;   // torchvision devIoU with a = the higher-scored box
+                const float sa = row_a ? rr.area : qarea;
+                const float bw = row_a ? qw : (r.z - r.x), bh = row_a ? qh : (r.w - r.y);
+                const float den = __fmaf_rn(bw, bh, sa) - inter;
+                pr = (inter / den) > thr;
+            }
+            fin = pr && qp > I * kTile + i && (!class_mode || scls[qp] == rr.cls);
+            rlo = min(rr.rank, crank);
+            rhi = max(rr.rank, crank);
+        }
+        const unsigned em = __ballot_sync(0xffffffffu, fin);
+        if (em) {
+            if (fin) w.ebuf[n_buf + __popc(em & lt_mask)] = make_uint2(rlo, rhi);
+            n_buf += __popc(em);
+            if (n_buf > kTile) edge_flush(a, w, b, edges, n_buf);  // no room for another 32
+        }
+    }
+    __syncwarp();
+    n_cand = 0;
+}
 
-    // this lane's column
-    const u32* sub = w.sub + head;  // the chunk's four sub-tile ids (kNoSub = empty slot)
-    const u32 my_sub = sub[grp];
-    const bool slot_ok = my_sub != kNoSub;
-    const int cp = slot_ok ? (int)(my_sub * kSub) + (lane & (kSub - 1)) : 0;
-    const bool cvalid = slot_ok && cp < M;
-    float4 cq = make_float4(far, far, far, far);
-    RowAux cx = {0xffffffffu, 0u};
-    if (cvalid) { cq = sb[cp]; cx.rank = srank[cp]; cx.cls = scls[cp]; }
-    const float cw = cq.z - cq.x, ch = cq.w - cq.y;
-    w.col[lane] = cq;
-    w.carea[lane] = cw * ch;
-    w.caux[lane] = cx;
+// One chunk = up to 8 sub-tiles (8 columns each) that survived the tile-level tests against row tile I.
+// Lane l stages columns 2*(l&3), +1 of slot l>>2 as one packed record.  Rows are culled against each slot's
+// statistics (one half2 step per dimension pair), the surviving (row, slot) items are packed, and every
+// iteration of the pair loop filters 8 items x 8 columns: 64 pairs on 32 lanes whatever the culling pattern.
+__device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I, int head,
+                                           const float4* __restrict__ sb, const u32* __restrict__ srank,
+                                           const u32* __restrict__ scls, uint2* __restrict__ edges, const Frame& f,
+                                           const int n_slots, const bool rvalid, const u32 r_lo, const u32 r_hi,
+                                           const u32 r_wh_t, const u32 r_ar, u32& n_evals, u32& n_cands,
+                                           int& n_cand, int& n_buf) {
+    const int lane = threadIdx.x & 31;
+    const int grp = lane >> 2, j = lane & 3;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int M = info.M;
+    const u32* sub = w.sub + head;  // the chunk's eight sub-tile ids (kNoSub = empty slot)
 
-    // row culling against the statistics of each slot; pack the surviving (row, slot) items
-    int n_items = 0;
+    // ---- this lane's two columns, in the row tile's frame ----
+    {
+        const u32 e = sub[grp];
+        const int cp = (int)(e * kSub) + 2 * j;
+        const __half far_lo = __float2half_rz(1000.0f), far_hi = __float2half_rz(-1000.0f), one = __float2half_rz(1.0f);
+        __half x1[2] = {far_lo, far_lo}, y1[2] = {far_lo, far_lo}, x2[2] = {far_hi, far_hi}, y2[2] = {far_hi, far_hi};
+        __half ar[2] = {one, one};
+        if (e != kNoSub) {
 #pragma unroll
-    for (int s = 0; s < kSubs; ++s) {
-        const u32 e = sub[s];
-        bool rok = rvalid && e != kNoSub;
-        if (rok) {
-            if (prune) {
-                const float4 sbx = w.sbx[head + s];
-                const float2 sar = w.sar[head + s];
-                const float ox = fminf(rq.z, sbx.z) - fmaxf(rq.x, sbx.x);
-                const float oy = fminf(rq.w, sbx.w) - fmaxf(rq.y, sbx.y);
-                rok = ox > 0.0f && oy > 0.0f && ox >= rw_t && oy >= rh_t && sar.y >= rS_t && rS >= t2 * sar.x;
-            } else {
-                rok = (int)(e * kSub) < M;
+            for (int h = 0; h < 2; ++h) {
+                if (cp + h < M) {
+                    const float4 q = sb[cp + h];
+                    x1[h] = __float2half_rd(__fmaf_rd(q.x, f.S, f.nox));
+                    y1[h] = __float2half_rd(__fmaf_rd(q.y, f.S, f.noy));
+                    x2[h] = __float2half_ru(__fmaf_ru(q.z, f.S, f.nox));
+                    y2[h] = __float2half_ru(__fmaf_ru(q.w, f.S, f.noy));
+                    ar[h] = area16_down(q, f);
+                }
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, rok);
-        if (rok) w.item[n_items + __popc(m & lt_mask)] = (unsigned short)((s << 11) | (lane << 5));
-        n_items += __popc(m);
+        Rec16& c = w.col16[lane];
+        c.box = make_uint4(pack_h2(x1[0], x1[1]), pack_h2(y1[0], y1[1]), pack_h2(x2[0], x2[1]), pack_h2(y2[0], y2[1]));
+        c.area = pack_h2(ar[0], ar[1]);
     }
-    if (lane < kSubs) w.item[n_items + lane] = (unsigned short)(kTile << 5);  // pad with the sentinel row
+
+    // ---- row culling against the statistics of each slot; pack the surviving (row, slot) items ----
+    int n_items = 0;
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+        if (s < n_slots) {   // warp-uniform: the valid slots of a chunk are a prefix
+            const uint2 sbx = w.sbx[head + s];
+            const __half2 o = __hsub2(__hmin2(as_h2(r_hi), as_h2(sbx.y)), __hmax2(as_h2(r_lo), as_h2(sbx.x)));
+            const bool rok = rvalid & h2_all_ge(as_u32(o), r_wh_t) & h2_all_ge(w.sar[head + s], r_ar);
+            const unsigned m = __ballot_sync(0xffffffffu, rok);
+            if (rok) w.item[n_items + __popc(m & lt_mask)] = ((u32)(s * 4 * (int)sizeof(Rec16)) << 16) | (u32)(lane * (int)sizeof(Rec16));
+            n_items += __popc(m);
+        }
+    }
+    if (lane < kSlots) w.item[n_items + lane] = (u32)(kTile * (int)sizeof(Rec16));  // pad with the sentinel row (slot 0)
     n_evals += (u32)n_items;
     __syncwarp();
 
-    const float thr = a.thr;
-    const float4* colp = w.col + (lane & (kSub - 1));
-    const float* careap = w.carea + (lane & (kSub - 1));
-    for (int it = 0; it < n_items; it += kSubs) {
+    // ---- half-precision filter: 8 items x 8 columns per iteration ----
+    const __half2 K = as_h2(a.k16x2);
+    const __half2 zero = as_h2(0u);
+    const char* rowbase = reinterpret_cast<const char*>(w.row16);
+    const char* colbase = reinterpret_cast<const char*>(w.col16) + j * sizeof(Rec16);
+    for (int it = 0; it < n_items; it += kSlots) {
         const u32 item = w.item[it + grp];
-        const int slot = item >> 11;
-        const int c = slot * kSub;
-        const RowRec* rr = reinterpret_cast<const RowRec*>(reinterpret_cast<const char*>(w.row) + (item & 0x7e0u));
-        const float4 r = rr->box;
-        const float rarea = rr->area;
-        const float4 q = colp[c];
-        const float qarea = careap[c];
-        const float left = fmaxf(r.x, q.x), right = fminf(r.z, q.z);
-        const float top = fmaxf(r.y, q.y), bottom = fminf(r.w, q.w);
-        const float iw = fmaxf(right - left, 0.0f), ih = fmaxf(bottom - top, 0.0f);
-        const float inter = iw * ih;
-        // den within a few ulp of torchvision's fma form whichever box plays `a`: inside the margin
-        // (the sentinel row has zero area and no overlap: d = -tt, never positive)
-        const float den0 = (qarea + rarea) - inter;
-        const float tt = thr * den0;
-        const float d = inter - tt;
-        bool pr = d > 0.0f;
-        const bool amb = all_exact || !(fabsf(d) > __fmaf_rn(tt, kEps, kTiny));
-        if (!__any_sync(0xffffffffu, pr || amb)) continue;
-        // rare: a candidate edge.  Exact arithmetic where needed, validity, same class, each pair once.
-        const bool act = it + grp < n_items;  // padding items (sentinel row) never make an edge
-        const int i = (int)((item >> 5) & 63u);
-        const RowAux ra = {rr->rank, rr->cls};
-        const int qp = (int)(sub[slot] * kSub) + (lane & (kSub - 1));
-        const bool qvalid = act && qp < M;
-        const RowAux ca = w.caux[c + (lane & (kSub - 1))];
-        const u32 crank = ca.rank, ccls = ca.cls;
-        if (amb) {
-            // torchvision devIoU with a = the higher-scored box
-            const bool row_a = ra.rank < crank;
-            const float qw = q.z - q.x, qh = q.w - q.y;
-            const float sa = row_a ? rarea : qarea;
-            const float bw = row_a ? qw : (r.z - r.x), bh = row_a ? qh : (r.w - r.y);
-            const float den = __fmaf_rn(bw, bh, sa) - inter;
-            pr = (inter / den) > thr;
-        }
-        const bool fin = pr && qvalid && (!class_mode || ccls == ra.cls) && qp > I * kTile + i;
-        const unsigned em = __ballot_sync(0xffffffffu, fin);
-        if (em) {
-            if (fin) w.ebuf[n_buf + __popc(em & lt_mask)] = make_uint2(min(ra.rank, crank), max(ra.rank, crank));
-            n_buf += __popc(em);
-            if (n_buf > kTile) edge_flush(a, w, b, edges, n_buf);  // no room for another 32
+        const Rec16* rr = reinterpret_cast<const Rec16*>(rowbase + (item & 0xffffu));
+        const Rec16* cc = reinterpret_cast<const Rec16*>(colbase + (item >> 16));
+        const uint4 R = rr->box, C = cc->box;
+        const __half2 iw = __hmax2(__hsub2(__hmin2(as_h2(R.z), as_h2(C.z)), __hmax2(as_h2(R.x), as_h2(C.x))), zero);
+        const __half2 ih = __hsub2(__hmin2(as_h2(R.w), as_h2(C.w)), __hmax2(as_h2(R.y), as_h2(C.y)));
+        const __half2 sum = __hadd2(as_h2(rr->area), as_h2(cc->area));
+        const __half2 x = __hfma2(__hmul2(iw, ih), K, __hneg2(sum));
+        const u32 hit = h2_ge0_bits(as_u32(x));   // bit h: column h of this lane may be an edge (NaN: no overlap at all)
+        if (!__any_sync(0xffffffffu, hit != 0u)) continue;
+        // queue the candidates (two ballots: first and second column of every lane)
+        const int i = (int)((item & 0xffffu) / (u32)sizeof(Rec16));
+        const int qp = (int)(sub[item >> 23] * kSub) + 2 * j;   // slot = (item >> 16) / 128
+        const bool c0 = (hit & 1u) && i < kTile && qp < M;
+        const bool c1 = (hit & 2u) && i < kTile && qp + 1 < M;
+        const unsigned m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
+        if (c0) w.cand[n_cand + __popc(m0 & lt_mask)] = ((u32)i << 24) | (u32)qp;
+        n_cand += __popc(m0);
+        if (c1) w.cand[n_cand + __popc(m1 & lt_mask)] = ((u32)i << 24) | (u32)(qp + 1);
+        n_cand += __popc(m1);
+        if (n_cand >= kTile) {
+            n_cands += (u32)n_cand;
+            cand_process(a, w, info, b, I, sb, srank, scls, edges, n_cand, n_buf);
         }
     }
     __syncwarp();
 }
 
 __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs a) {
-    __shared__ EdgeWarp s_w[kEdgeThreads / 32];
+    __shared__ __align__(16) EdgeWarp s_w[kEdgeThreads / 32];
     const int lane = threadIdx.x & 31;
     EdgeWarp& w = s_w[threadIdx.x >> 5];
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -442,11 +536,11 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
     const float far = 3.0e38f;
 
     for (;;) {
-        u32 item = 0;
-        if (lane == 0) item = atomicAdd(a.ticket, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= total) break;
-        const int I = (int)(item / (u32)a.B), b = (int)(item % (u32)a.B);  // all images' tile 0 first
+        u32 ticket = 0;
+        if (lane == 0) ticket = atomicAdd(a.ticket, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= total) break;
+        const int I = (int)(ticket / (u32)a.B), b = (int)(ticket % (u32)a.B);  // all images' tile 0 first
         const GImg info = a.info[b];
         if (I >= info.n_tiles || info.overflow) continue;
         const int M = info.M;
@@ -457,36 +551,77 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         const float4* ts = a.tstat + (size_t)b * a.tcap * 2;
         const float4* ss = a.sstat + (size_t)b * a.tcap * kSubs * 2;
         uint2* edges = a.edges + (u64)b * a.edges_per_img;
-        const bool prune = info.t2 >= 0.0f;
         const float t2 = info.t2;
+        const float t3 = a.t3;
         const bool class_mode = info.mode == G_CLASS;
 
-        // this lane's row of tile I
+        // ---- the tile's local frame ----
+        const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
+        Frame f;
+        {
+            const float ext = fmaxf(ib.z - ib.x, ib.w - ib.y) * 0.5f;
+            int k = a.hexp - ((int)((__float_as_uint(ext) >> 23) & 255u) - 127);   // ext * 2^k in [2^hexp, 2^(hexp+1))
+            k = max(-60, min(60, k));
+            f.S = __int_as_float((127 + k) << 23);
+            f.S2 = f.S * f.S;
+            f.nox = -((ib.x + ib.z) * 0.5f) * f.S;
+            f.noy = -((ib.y + ib.w) * 0.5f) * f.S;
+        }
+        const u32 icmin = __float_as_uint(ia.z), icmax = __float_as_uint(ia.w);
+
+        // ---- this lane's row of tile I: fp32 record for the exact stage, packed record for the filter ----
         const int rp = I * kTile + lane;
         const bool rvalid = rp < M;
         float4 rq = make_float4(-far, -far, -far, -far);
         u32 rrank = 0xffffffffu, rcls = 0u;
         if (rvalid) { rq = sb[rp]; rrank = srank[rp]; rcls = scls[rp]; }
-        const float rw = rq.z - rq.x, rh = rq.w - rq.y;
-        const float rS = rw * rh;
-        const float rw_t = t2 * rw, rh_t = t2 * rh, rS_t = t2 * rS;
+        u32 r_lo, r_hi, r_wh_t, r_ar;
         __syncwarp();
-        w.row[lane] = RowRec{rq, rS, rrank, rcls, 0u};
-        if (lane == 0) w.row[kTile] = RowRec{make_float4(-far, -far, -far, -far), 0.0f, 0xffffffffu, 0u, 0u};
+        {
+            const __half s_lo = __float2half_rz(1000.0f), s_hi = __float2half_rz(-1000.0f);
+            __half x1 = s_lo, y1 = s_lo, x2 = s_hi, y2 = s_hi, ar = __float2half_rz(1.0f);
+            __half wt = s_lo, ht = s_lo, at = s_lo, au = s_hi;
+            if (rvalid) {
+                x1 = __float2half_rd(__fmaf_rd(rq.x, f.S, f.nox));
+                y1 = __float2half_rd(__fmaf_rd(rq.y, f.S, f.noy));
+                x2 = __float2half_ru(__fmaf_ru(rq.z, f.S, f.nox));
+                y2 = __float2half_ru(__fmaf_ru(rq.w, f.S, f.noy));
+                ar = area16_down(rq, f);
+                wt = __float2half_rz(__fmul_rd(__fmul_rd(__fsub_rd(rq.z, rq.x), f.S), t3));
+                ht = __float2half_rz(__fmul_rd(__fmul_rd(__fsub_rd(rq.w, rq.y), f.S), t3));
+                const float up = area_up(rq, f);
+                at = __float2half_rz(__fmul_rd(__fmul_rd(__fmul_rd(__fsub_rd(rq.z, rq.x), __fsub_rd(rq.w, rq.y)), f.S2), t3));
+                au = __hneg(__float2half_ru(up));
+            }
+            r_lo = pack_h2(x1, y1);
+            r_hi = pack_h2(x2, y2);
+            r_wh_t = pack_h2(wt, ht);
+            r_ar = pack_h2(at, au);          // slot {amax up, -(t3*amin) down} >= {t3*area down, -(area up)}
+            w.rowf[lane] = RowF{rq, (rq.z - rq.x) * (rq.w - rq.y), rrank, rcls, 0u};
+            Rec16& r16 = w.row16[lane];
+            r16.box = make_uint4(pack_h2(x1, x1), pack_h2(y1, y1), pack_h2(x2, x2), pack_h2(y2, y2));
+            r16.area = pack_h2(ar, ar);
+            if (lane == 0) {
+                Rec16& sen = w.row16[kTile];
+                sen.box = make_uint4(pack_h2(s_lo, s_lo), pack_h2(s_lo, s_lo), pack_h2(s_hi, s_hi), pack_h2(s_hi, s_hi));
+                sen.area = pack_h2(__float2half_rz(1.0f), __float2half_rz(1.0f));
+            }
+        }
         __syncwarp();
-        const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
-        const u32 icmin = __float_as_uint(ia.z), icmax = __float_as_uint(ia.w);
-        u32 n_evals = 0;
-        int n_q = 0;    // sub-tiles waiting in w.sub
-        int n_buf = 0;  // edges waiting in w.ebuf
+        u32 n_evals = 0, n_cands = 0;
+        int n_q = 0;     // sub-tiles waiting in w.sub
+        int n_buf = 0;   // edges waiting in w.ebuf
+        int n_cand = 0;  // filter survivors waiting in w.cand
 
         for (int J0 = I;; J0 += 32) {
             const bool tail = J0 >= info.n_tiles;  // one extra round flushes the last partial chunk
             int n_t = 0;
+            int n_tail = kSlots;   // valid slots of the chunk about to be processed (< kSlots only in the tail)
             if (tail) {
                 if (n_q == 0) break;
-                if (lane >= n_q && lane < kSubs) w.sub[lane] = kNoSub;
-                n_q = kSubs;
+                if (lane >= n_q && lane < kSlots) w.sub[lane] = kNoSub;
+                n_tail = n_q;
+                n_q = kSlots;
                 __syncwarp();
             } else {
                 // level 1: lane <-> tile J
@@ -503,7 +638,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                         continue;
                     }
                 }
-                if (ok && prune) {
+                if (ok) {
                     ok = fminf(ib.z, jb.z) > fmaxf(ib.x, jb.x) && fminf(ib.w, jb.w) > fmaxf(ib.y, jb.y) &&
                          ia.y >= t2 * ja.x && ja.y >= t2 * ia.x;
                 }
@@ -524,7 +659,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                     if (sok) {
                         e = w.tl[k] * kSubs + (u32)(lane & (kSubs - 1));
                         sok = (int)(e * kSub) < M;
-                        if (sok && prune) {
+                        if (sok) {
                             sbx = ss[e * 2]; sar = ss[e * 2 + 1];
                             sok = fminf(ib.z, sbx.z) > fmaxf(ib.x, sbx.x) && fminf(ib.w, sbx.w) > fmaxf(ib.y, sbx.y) &&
                                   ia.y >= t2 * sar.x && sar.y >= t2 * ia.x;
@@ -534,22 +669,26 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                     if (sok) {
                         const int qi = n_q + __popc(sm & lt_mask);
                         w.sub[qi] = e;
-                        w.sbx[qi] = sbx;
-                        w.sar[qi] = make_float2(sar.x, sar.y);
+                        // statistics in the local frame, rounded so that the row test can only pass more often
+                        const __half bx1 = __float2half_rd(__fmaf_rd(sbx.x, f.S, f.nox)), by1 = __float2half_rd(__fmaf_rd(sbx.y, f.S, f.noy));
+                        const __half bx2 = __float2half_ru(__fmaf_ru(sbx.z, f.S, f.nox)), by2 = __float2half_ru(__fmaf_ru(sbx.w, f.S, f.noy));
+                        w.sbx[qi] = make_uint2(pack_h2(bx1, by1), pack_h2(bx2, by2));
+                        const __half amax = __float2half_ru(__fmul_ru(__fmul_ru(sar.y, 1.0000077f), f.S2));
+                        const __half amin = __float2half_rz(__fmul_rd(__fmul_rd(__fmul_rd(sar.x, 0.9999923f), f.S2), t3));
+                        w.sar[qi] = pack_h2(amax, __hneg(amin));
                     }
                     n_q += __popc(sm);
                     __syncwarp();
                 }
-                // level 3: chunks of 4 sub-tiles
+                // level 3: chunks of 8 sub-tiles
                 int head = 0;
-                for (; n_q - head >= kSubs; head += kSubs)
-                    edge_chunk(a, w, info, b, I, head, sb, srank, scls, edges, rq, rvalid, rw_t, rh_t, rS, rS_t, n_evals,
-                               n_buf);
-                if (head) {  // move the < 4 leftovers to the front
+                for (; n_q - head >= kSlots; head += kSlots)
+                    edge_chunk(a, w, info, b, I, head, sb, srank, scls, edges, f, n_tail, rvalid, r_lo, r_hi, r_wh_t, r_ar,
+                               n_evals, n_cands, n_cand, n_buf);
+                if (head) {  // move the < 8 leftovers to the front
                     const int rem = n_q - head;
-                    u32 v = 0u;
-                    float4 vb = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float2 va = make_float2(0.f, 0.f);
+                    u32 v = 0u, va = 0u;
+                    uint2 vb = make_uint2(0u, 0u);
                     if (lane < rem) { v = w.sub[head + lane]; vb = w.sbx[head + lane]; va = w.sar[head + lane]; }
                     __syncwarp();
                     if (lane < rem) { w.sub[lane] = v; w.sbx[lane] = vb; w.sar[lane] = va; }
@@ -559,8 +698,15 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                 t0 += 32 / kSubs;
             } while (t0 < n_t);
         }
+        if (n_cand) {
+            n_cands += (u32)n_cand;
+            cand_process(a, w, info, b, I, sb, srank, scls, edges, n_cand, n_buf);
+        }
         edge_flush(a, w, b, edges, n_buf);
-        if (lane == 0 && n_evals) atomicAdd(&a.info[b].n_evals, (unsigned long long)n_evals);
+        if (lane == 0 && n_evals) {
+            atomicAdd(&a.info[b].n_evals, (unsigned long long)n_evals);
+            atomicAdd(&a.info[b].n_cands, (unsigned long long)n_cands);
+        }
     }
 }
 
@@ -837,7 +983,16 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     a.boxes = reinterpret_cast<const float4*>(boxes); a.scores = scores; a.classes = classes; a.counts = counts;
     a.B = B; a.cap = cap; a.tcap = (cap + kTile - 1) / kTile;
     a.thr = (float)iou_threshold;
-    a.thr_fast_ok = (a.thr >= 0.0f && a.thr <= 1e30f) ? 1 : 0;
+    a.thr_fast_ok = (a.thr >= 0.03f && a.thr <= 1e30f) ? 1 : 0;
+    a.t3 = a.thr * (1.0f - 0.015625f);
+    {
+        // K = (1+th)/th with 2^-6 of slack, rounded up into a half; the filter keeps a pair iff K*inter >= area_a + area_b
+        const double th = (double)a.thr * (1.0 - 1.0 / 4096.0);
+        const double K = a.thr_fast_ok ? (1.0 + th) / th * (1.0 + 1.0 / 64.0) * (1.0 + 1.0 / 512.0) : 1.0;
+        const unsigned short kb = __half_as_ushort(__float2half_rn((float)K));   // rn error 2^-11 < the 2^-9 bias above
+        a.k16x2 = (u32)kb | ((u32)kb << 16);
+        a.hexp = a.thr >= 0.35f ? 5 : (a.thr >= 0.1f ? 4 : 3);   // keeps K * (row area) inside the half range
+    }
     a.trick_max_numel = trick_max_numel;
     a.k0 = (u32*)(w + L.k[0]); a.v0 = (u32*)(w + L.k[1]); a.k1 = (u32*)(w + L.k[2]);
     a.v1 = (u32*)(w + L.k[3]); a.k2 = (u32*)(w + L.k[4]); a.v2 = (u32*)(w + L.k[5]);
@@ -876,17 +1031,18 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
 }
 
 int graph_stats(const void* ws, size_t ws_bytes, int B, int cap, unsigned long long* evals, unsigned long long* edges,
-                cudaStream_t st) {
+                unsigned long long* cands, cudaStream_t st) {
     GLayout L = graph_layout(B, cap);
     YB_CHECK_ARG(ws && ws_bytes >= L.total, "nms_graph_stats: not a graph workspace");
     std::vector<GImg> h((size_t)B);
     YB_CUDA(cudaMemcpyAsync(h.data(), reinterpret_cast<const char*>(ws) + L.info, (size_t)B * sizeof(GImg),
                             cudaMemcpyDeviceToHost, st));
     YB_CUDA(cudaStreamSynchronize(st));
-    unsigned long long ev = 0, ed = 0;
-    for (auto& g : h) { ev += g.n_evals * (unsigned long long)kSub; ed += g.n_edges; }  // items -> pair tests
+    unsigned long long ev = 0, ed = 0, ca = 0;
+    for (auto& g : h) { ev += g.n_evals * (unsigned long long)kSub; ed += g.n_edges; ca += g.n_cands; }  // items -> pair tests
     if (evals) *evals = ev;
     if (edges) *edges = ed;
+    if (cands) *cands = ca;
     return 0;
 }
 

@@ -682,17 +682,18 @@ def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_
 
 
 def nms_graph_stats(det):
-    """(pair tests executed, edges) of the graph NMS behind a `detect_batch` result, summed over the
-    batch; None for the bitmask algorithm.  Synchronises.  For bench.py / tests."""
+    """(pair tests executed by the half-precision filter, edges, pairs decided exactly in fp32) of the graph NMS
+    behind a `detect_batch` result, summed over the batch; None for the bitmask algorithm.  Synchronises.
+    For bench.py / tests."""
     ws = det.get("nms_ws")
     if ws is None or det.get("algo", NMS_GRAPH) != NMS_GRAPH:
         return None
     B, cap = det["boxes"].shape[0], det["boxes"].shape[1]
-    ev, ed = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    ev, ed, ca = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
     with torch.cuda.device(ws.device):
         _lib.check(_lib.lib().yb_nms_graph_stats(ws.data_ptr(), ws.numel(), B, cap, ctypes.byref(ev), ctypes.byref(ed),
-                                                 _stream()), "yb_nms_graph_stats")
-    return int(ev.value), int(ed.value)
+                                                 ctypes.byref(ca), _stream()), "yb_nms_graph_stats")
+    return int(ev.value), int(ed.value), int(ca.value)
 
 
 def nms_retry_overflow(boxes, scores, classes, counts, iou_threshold, trick_max_numel, keep, n_keep):
