@@ -179,3 +179,66 @@ if __name__ == "__main__":
         print("wh key", wb, "bbox"); simulate(b, key_wh(b, wb, wb))
         print("wh key", wb, "wh stats"); simulate(b, key_wh(b, wb, wb), mode='wh')
     print("current key + wh stats"); simulate(b, key_current(b), mode='wh')
+
+
+def per_tile_cost(b, key, thr=0.4, tile=32, sub=8):
+    t2 = thr * (1 - 2 ** -10)
+    order = np.argsort(key, kind='stable')
+    sb = b[order]
+    Ts, Ss = stats(sb, tile), stats(sb, sub)
+    nT, nS = len(Ts['x1']), len(Ss['x1'])
+    k = tile // sub
+    l1 = group_vs_group(Ts, Ts, t2, 'bbox') & np.triu(np.ones((nT, nT), bool))
+    l2 = group_vs_group(Ts, Ss, t2, 'bbox') & np.repeat(l1, k, axis=1)[:, :nS]
+    return l1.sum(1), l2.sum(1)
+
+
+def hilbert(cx, cy, lo, hi, bits=8):
+    n = 1 << bits
+    qs = (n - 1) / (hi - lo)
+    x = np.clip((cx - lo) * qs, 0, n - 1).astype(np.int64)
+    y = np.clip((cy - lo) * qs, 0, n - 1).astype(np.int64)
+    d = np.zeros_like(x)
+    s = n // 2
+    while s > 0:
+        rx = ((x & s) > 0).astype(np.int64)
+        ry = ((y & s) > 0).astype(np.int64)
+        d += s * s * ((3 * rx) ^ ry)
+        # rotate
+        m = ry == 0
+        flip = m & (rx == 1)
+        x = np.where(flip, s - 1 - (x & (s - 1)) + (x & ~(s - 1)) * 0, x)  # placeholder, fixed below
+        s //= 2
+    return d
+
+
+def hilbert_d(cx, cy, lo, hi, bits=8):
+    """classic xy2d"""
+    n = 1 << bits
+    qs = (n - 1) / (hi - lo)
+    x = np.clip((cx - lo) * qs, 0, n - 1).astype(np.int64)
+    y = np.clip((cy - lo) * qs, 0, n - 1).astype(np.int64)
+    d = np.zeros_like(x)
+    s = n // 2
+    while s > 0:
+        rx = ((x & s) > 0).astype(np.int64)
+        ry = ((y & s) > 0).astype(np.int64)
+        d += s * s * ((3 * rx) ^ ry)
+        m = ry == 0
+        fl = m & (rx == 1)
+        x2 = np.where(fl, n - 1 - x, x)
+        y2 = np.where(fl, n - 1 - y, y)
+        x, y = np.where(m, y2, x2), np.where(m, x2, y2)
+        s //= 2
+    return d.astype(np.uint64)
+
+
+def key_variant(b, curve='morton', alternate=False):
+    area = ((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])).astype(np.float32)
+    bucket = ((area.view(np.uint32) >> 24) & 0x7f).astype(np.uint64)
+    cx, cy = (b[:, 0] + b[:, 2]) * 0.5, (b[:, 1] + b[:, 3]) * 0.5
+    lo, hi = min(cx.min(), cy.min()), max(cx.max(), cy.max())
+    c = morton(cx, cy, lo, hi).astype(np.uint64) if curve == 'morton' else hilbert_d(cx, cy, lo, hi)
+    if alternate:
+        c = np.where(bucket & 1, np.uint64(0xffff) - c, c)
+    return (bucket << np.uint64(16)) | c

@@ -58,7 +58,7 @@ struct GArgs {
     const float* scores;
     const int64_t* classes;
     const int* counts;
-    int B, cap, tcap;
+    int B, cap, tcap, scap;   // scap: per-image stride of sboxes (cap rounded up to a whole sub-tile)
     float thr;
     int thr_fast_ok;
     float t3;       // thr * (1 - 2^-6): threshold of the half-precision culling tests
@@ -104,15 +104,38 @@ __device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float
     return r;
 }
 
-// spatial sort key: (class | area octave pair | Morton(centre))
+// Hilbert index of an 8-bit cell (x, y): a CONTINUOUS space-filling curve, so 32 consecutive boxes never jump
+// across the image the way the Z-order's quadrant changes make them (those tiles had bounding boxes spanning
+// half the image and did 3x the average work).
+__device__ __forceinline__ u32 hilbert8(u32 x, u32 y) {
+    u32 d = 0;
+#pragma unroll
+    for (u32 s = 128u; s > 0u; s >>= 1) {
+        const u32 rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0u) {
+            if (rx == 1u) { x = 255u - x; y = 255u - y; }
+            const u32 t = x; x = y; y = t;
+        }
+    }
+    return d;
+}
+
+// spatial sort key: (class | area bucket of 1.5 octaves | Hilbert index of the centre, direction alternating
+// with the bucket's parity so that a tile straddling two buckets stays in one corner of the image).
+// tools/nms_cull_sim.py on the bench workload, per image: sub-tile pairs 30.3 K -> 17.9 K, (row, sub-tile)
+// items 161 K -> 119 K, heaviest row tile 842 -> 160 sub-tile pairs, against the round-1 key (2-octave bucket,
+// Z-order).
 __device__ __forceinline__ u32 spatial_key(const float4 q, const int64_t* classes, int i, float cmin, float qs) {
     const float area = (q.z - q.x) * (q.w - q.y);
-    const u32 bucket = (__float_as_uint(area) >> 24) & 0x7fu;
+    const float lg = fminf(fmaxf(__log2f(area), -44.0f), 120.0f);   // area <= 0 or NaN -> lowest bucket
+    const u32 bucket = (u32)(int)floorf(lg * 0.6666667f + 32.0f) & 0x7fu;
     const float fx = fminf(fmaxf(((q.x + q.z) * 0.5f - cmin) * qs, 0.0f), 255.0f);
     const float fy = fminf(fmaxf(((q.y + q.w) * 0.5f - cmin) * qs, 0.0f), 255.0f);
-    const u32 mort = spread8((u32)fx) | (spread8((u32)fy) << 1);
+    u32 curve = hilbert8((u32)fx, (u32)fy);
+    if (bucket & 1u) curve ^= 0xffffu;
     const u32 c = classes ? ((u32)classes[i] & 0x1ffu) : 0u;
-    return (c << 23) | (bucket << 16) | mort;
+    return (c << 23) | (bucket << 16) | curve;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -247,6 +270,9 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
     const int p = t * kTile + lane;
     float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY, amin = INFINITY, amax = -INFINITY;
     u32 c0 = 0xffffffffu, c1 = 0u;
+    float4* sbo = a.sboxes + (size_t)b * a.scap;
+    if (p >= M && p < ((M + kSub - 1) & ~(kSub - 1)))   // the edge kernel stages whole sub-tiles: far-away padding boxes
+        sbo[p] = make_float4(1e18f, 1e18f, 2e18f, 2e18f);
     if (p < M) {
         const u32 idx = a.pos[off + p];
         float4 q = boxes[idx];
@@ -257,7 +283,7 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
             q.x += o; q.y += o; q.z += o; q.w += o;
         }
         const u32 cls = (info.mode == G_CLASS) ? c : 0u;
-        a.sboxes[off + p] = q;
+        sbo[p] = q;
         a.srank[off + p] = a.rinv[off + idx];
         a.scls[off + p] = cls;
         x1 = q.x; y1 = q.y; x2 = q.z; y2 = q.w;
@@ -303,11 +329,6 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
 // depends on the half-precision stage.  Images the filter cannot serve (NaN/Inf/inverted boxes, thresholds
 // outside [0.03, 1e30]) are not handled here at all: the resolve kernel's greedy pass decides them.
 // ------------------------------------------------------------------------------------------------
-struct RowF {  // 32 bytes: the fp32 row of the exact stage
-    float4 box;
-    float area;
-    u32 rank, cls, pad;
-};
 struct Rec16 {   // 32 bytes: a box (rows: the same box in both halves; columns: two neighbouring columns) in the
     uint4 box;   // row tile's local frame: half2 x1 | y1 | x2 | y2, corners rounded outwards
     u32 area;    // half2 area, rounded towards zero, capped at 32768; -60000 = "too small for the format"
@@ -316,31 +337,40 @@ struct Rec16 {   // 32 bytes: a box (rows: the same box in both halves; columns:
 constexpr int kSlots = 8;            // sub-tiles per chunk: 64 columns, two per lane
 constexpr int kQueue = kTile + 8;    // sub-tiles queued per level-2 step (<= 32) + < 8 left over
 constexpr int kCand = 3 * kTile;     // candidate queue: processed when >= 32, one iteration adds <= 64
+constexpr int kItems = kSlots * kTile + kSlots;
 struct EdgeWarp {
-    RowF rowf[kTile];
     Rec16 row16[kTile + 1];          // [kTile]: a sentinel that overlaps nothing (pads the item list)
     Rec16 col16[kSlots * 4];         // lane l of the chunk: columns 2*(l&3), +1 of slot l>>2
     u32 tl[kTile];                   // compaction scratch: surviving tiles of the current step
     u32 sub[kQueue];                 // queue of surviving sub-tile ids (J*kSubs+s) ...
     uint2 sbx[kQueue];               // ... their bounding boxes in the local frame: half2 {x1,y1} down | {x2,y2} up ...
     u32 sar[kQueue];                 // ... and half2 {max area up, -(t3 * min area) down}
-    u32 item[kSlots * kTile + kSlots];  // (slot * 128) << 16 | (row * 32): byte offsets of the item's column / row records
+    unsigned short irow[kItems];     // packed work list of a chunk: byte offset of the item's row record in row16 ...
+    unsigned short icol[kItems];     // ... and of its slot's first column record in col16
     u32 cand[kCand];                 // (row << 24) | column position: pairs that passed the half-precision filter
     uint2 ebuf[2 * kTile];           // edges found, flushed to the image's list 33..64 at a time
 };
 
-__device__ __forceinline__ u32 pack_h2(const __half lo, const __half hi) {
-    return (u32)__half_as_ushort(lo) | ((u32)__half_as_ushort(hi) << 16);
-}
+__device__ __forceinline__ u32 pack2(const unsigned short lo, const unsigned short hi) { return (u32)lo | ((u32)hi << 16); }
 __device__ __forceinline__ __half2 as_h2(const u32 v) { return *reinterpret_cast<const __half2*>(&v); }
 __device__ __forceinline__ u32 as_u32(const __half2 v) { return *reinterpret_cast<const u32*>(&v); }
-// both halves of a >= the halves of b (ordered: false on NaN): one HSETP2
+// float -> half bits with directed rounding (F2F.F16.F32.RM / .RP / .RZ)
+__device__ __forceinline__ unsigned short h_dn(const float v) { return __half_as_ushort(__float2half_rd(v)); }
+__device__ __forceinline__ unsigned short h_up(const float v) { return __half_as_ushort(__float2half_ru(v)); }
+__device__ __forceinline__ unsigned short h_rz(const float v) { return __half_as_ushort(__float2half_rz(v)); }
+// both halves of a >= the halves of b (ordered: false on NaN): one HSETP2 + PLOP3
 __device__ __forceinline__ bool h2_all_ge(const u32 a, const u32 b) {
     u32 r;
     asm("{\n\t.reg .pred p, q;\n\tsetp.ge.f16x2 p|q, %1, %2;\n\tand.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"(a), "r"(b));
     return r != 0u;
 }
-// either half of a >= 0 (ordered): bit 0 = low half, bit 1 = high half
+// either half of a >= 0 (ordered)
+__device__ __forceinline__ bool h2_any_ge0(const u32 a) {
+    u32 r;
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ge.f16x2 p|q, %1, %2;\n\tor.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"(a), "r"(0u));
+    return r != 0u;
+}
+// bit 0: low half of a >= 0, bit 1: high half (rare path)
 __device__ __forceinline__ u32 h2_ge0_bits(const u32 a) {
     u32 r;
     asm("{\n\t.reg .pred p, q;\n\t.reg .u32 t;\n\tsetp.ge.f16x2 p|q, %1, %2;\n\tselp.u32 %0, 1, 0, p;\n\tselp.u32 t, 2, 0, q;\n\tor.b32 %0, %0, t;\n\t}"
@@ -351,14 +381,11 @@ __device__ __forceinline__ u32 h2_ge0_bits(const u32 a) {
 struct Frame {   // local frame of a row tile
     float S, S2, nox, noy;   // scale (power of two), its square, -origin*S
 };
-// area of a nice box in the local frame: lower bound (towards zero), capped, tiny -> always-candidate marker
-__device__ __forceinline__ __half area16_down(const float4 q, const Frame& f) {
-    const float a = __fmul_rd(__fmul_rd(__fsub_rd(q.z, q.x), __fsub_rd(q.w, q.y)), f.S2);
-    if (!(a >= 2.44140625e-4f)) return __float2half_rz(-60000.0f);   // < 2^-12: products would leave the normal range
-    return __float2half_rz(fminf(a, 32768.0f));
-}
-__device__ __forceinline__ float area_up(const float4 q, const Frame& f) {
-    return __fmul_ru(__fmul_ru(__fsub_ru(q.z, q.x), __fsub_ru(q.w, q.y)), f.S2);
+// area of a nice box in the local frame as half bits: lower bound (towards zero), capped; boxes whose area
+// would leave the half format's normal range become unconditional candidates (marker -60000)
+__device__ __forceinline__ unsigned short area16_down(const float4 q, const float S2) {
+    const float a = __fmul_rd(__fmul_rd(__fsub_rd(q.z, q.x), __fsub_rd(q.w, q.y)), S2);
+    return a >= 2.44140625e-4f ? h_rz(fminf(a, 32768.0f)) : (unsigned short)0xfb53u;   // 0xfb53 = -60000 (rz)
 }
 
 // Append the warp's buffered edges to image b's list.
@@ -380,15 +407,16 @@ __device__ __forceinline__ void edge_flush(const GArgs& a, EdgeWarp& w, int b, u
 // Exact stage: the queued (row, column) pairs, one per lane.  torchvision's predicate with the division-free
 // margin test; ambiguous lanes redo the exact fma/div arithmetic with the higher-scored box as `a`.
 __device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I,
-                                             const float4* __restrict__ sb, const u32* __restrict__ srank,
-                                             const u32* __restrict__ scls, uint2* __restrict__ edges, int& n_cand,
-                                             int& n_buf) {
+                                          const float4* __restrict__ sb, const u32* __restrict__ srank,
+                                          const u32* __restrict__ scls, uint2* __restrict__ edges, int& n_cand,
+                                          int& n_buf) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float kEps = 9.5367431640625e-07f;     // 2^-20
     const float kTiny = 7.888609052210118e-31f;  // 2^-100
     const float thr = a.thr;
     const bool class_mode = info.mode == G_CLASS;
+    const int M = info.M;
     __syncwarp();
     for (int k0 = 0; k0 < n_cand; k0 += 32) {
         const int k = k0 + lane;
@@ -396,33 +424,34 @@ __device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const 
         u32 rlo = 0u, rhi = 0u;
         if (k < n_cand) {
             const u32 e = w.cand[k];
-            const int i = (int)(e >> 24);
+            const int rp = I * kTile + (int)(e >> 24);
             const int qp = (int)(e & 0xffffffu);
-            const RowF rr = w.rowf[i];
-            const float4 r = rr.box;
-            const float4 q = sb[qp];
-            const u32 crank = srank[qp];
-            const float qw = q.z - q.x, qh = q.w - q.y;
-            const float qarea = qw * qh;
-            const float left = fmaxf(r.x, q.x), right = fminf(r.z, q.z);
-            const float top = fmaxf(r.y, q.y), bottom = fminf(r.w, q.w);
-            const float iw = fmaxf(right - left, 0.0f), ih = fmaxf(bottom - top, 0.0f);
-            const float inter = iw * ih;
-            // den within a few ulp of torchvision's fma form whichever box plays `a`: inside the margin
-            const float den0 = (qarea + rr.area) - inter;
-            const float tt = thr * den0;
-            const float d = inter - tt;
-            bool pr = d > 0.0f;
-            if (!(fabsf(d) > __fmaf_rn(tt, kEps, kTiny))) {
-                const bool row_a = rr.rank < crank;   // torchvision devIoU with a = the higher-scored box
-                const float sa = row_a ? rr.area : qarea;
-                const float bw = row_a ? qw : (r.z - r.x), bh = row_a ? qh : (r.w - r.y);
-                const float den = __fmaf_rn(bw, bh, sa) - inter;
-                pr = (inter / den) > thr;
+            if (qp > rp && qp < M && rp < M) {   // each unordered pair once; padding columns of the last sub-tile never
+                const float4 r = sb[rp];
+                const float4 q = sb[qp];
+                const u32 rrank = srank[rp], crank = srank[qp];
+                const float qw = q.z - q.x, qh = q.w - q.y, rw = r.z - r.x, rh = r.w - r.y;
+                const float qarea = qw * qh, rarea = rw * rh;
+                const float left = fmaxf(r.x, q.x), right = fminf(r.z, q.z);
+                const float top = fmaxf(r.y, q.y), bottom = fminf(r.w, q.w);
+                const float iw = fmaxf(right - left, 0.0f), ih = fmaxf(bottom - top, 0.0f);
+                const float inter = iw * ih;
+                // den within a few ulp of torchvision's fma form whichever box plays `a`: inside the margin
+                const float den0 = (qarea + rarea) - inter;
+                const float tt = thr * den0;
+                const float d = inter - tt;
+                bool pr = d > 0.0f;
+                if (!(fabsf(d) > __fmaf_rn(tt, kEps, kTiny))) {
+                    const bool row_a = rrank < crank;   // torchvision devIoU with a = the higher-scored box
+                    const float sa = row_a ? rarea : qarea;
+                    const float bw = row_a ? qw : rw, bh = row_a ? qh : rh;
+                    const float den = __fmaf_rn(bw, bh, sa) - inter;
+                    pr = (inter / den) > thr;
+                }
+                fin = pr && (!class_mode || scls[qp] == scls[rp]);
+                rlo = min(rrank, crank);
+                rhi = max(rrank, crank);
             }
-            fin = pr && qp > I * kTile + i && (!class_mode || scls[qp] == rr.cls);
-            rlo = min(rr.rank, crank);
-            rhi = max(rr.rank, crank);
         }
         const unsigned em = __ballot_sync(0xffffffffu, fin);
         if (em) {
@@ -448,36 +477,31 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 2, j = lane & 3;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int M = info.M;
     const u32* sub = w.sub + head;  // the chunk's eight sub-tile ids (kNoSub = empty slot)
 
-    // ---- this lane's two columns, in the row tile's frame ----
+    // ---- this lane's two columns, in the row tile's frame (positions up to the end of the last sub-tile hold
+    //      far-away padding boxes: graph_gather_kernel) ----
     {
         const u32 e = sub[grp];
-        const int cp = (int)(e * kSub) + 2 * j;
-        const __half far_lo = __float2half_rz(1000.0f), far_hi = __float2half_rz(-1000.0f), one = __float2half_rz(1.0f);
-        __half x1[2] = {far_lo, far_lo}, y1[2] = {far_lo, far_lo}, x2[2] = {far_hi, far_hi}, y2[2] = {far_hi, far_hi};
-        __half ar[2] = {one, one};
+        uint4 box = make_uint4(0x63d063d0u, 0x63d063d0u, 0xe3d0e3d0u, 0xe3d0e3d0u);   // +1000 | -1000: overlaps nothing
+        u32 area = 0x3c003c00u;                                                          // 1.0
         if (e != kNoSub) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (cp + h < M) {
-                    const float4 q = sb[cp + h];
-                    x1[h] = __float2half_rd(__fmaf_rd(q.x, f.S, f.nox));
-                    y1[h] = __float2half_rd(__fmaf_rd(q.y, f.S, f.noy));
-                    x2[h] = __float2half_ru(__fmaf_ru(q.z, f.S, f.nox));
-                    y2[h] = __float2half_ru(__fmaf_ru(q.w, f.S, f.noy));
-                    ar[h] = area16_down(q, f);
-                }
-            }
+            const float4* src = sb + (size_t)e * kSub + 2 * j;
+            const float4 q0 = src[0], q1 = src[1];
+            box.x = pack2(h_dn(__fmaf_rd(q0.x, f.S, f.nox)), h_dn(__fmaf_rd(q1.x, f.S, f.nox)));
+            box.y = pack2(h_dn(__fmaf_rd(q0.y, f.S, f.noy)), h_dn(__fmaf_rd(q1.y, f.S, f.noy)));
+            box.z = pack2(h_up(__fmaf_ru(q0.z, f.S, f.nox)), h_up(__fmaf_ru(q1.z, f.S, f.nox)));
+            box.w = pack2(h_up(__fmaf_ru(q0.w, f.S, f.noy)), h_up(__fmaf_ru(q1.w, f.S, f.noy)));
+            area = pack2(area16_down(q0, f.S2), area16_down(q1, f.S2));
         }
         Rec16& c = w.col16[lane];
-        c.box = make_uint4(pack_h2(x1[0], x1[1]), pack_h2(y1[0], y1[1]), pack_h2(x2[0], x2[1]), pack_h2(y2[0], y2[1]));
-        c.area = pack_h2(ar[0], ar[1]);
+        c.box = box;
+        c.area = area;
     }
 
     // ---- row culling against the statistics of each slot; pack the surviving (row, slot) items ----
     int n_items = 0;
+    const unsigned short my_row = (unsigned short)(lane * (int)sizeof(Rec16));
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
         if (s < n_slots) {   // warp-uniform: the valid slots of a chunk are a prefix
@@ -485,11 +509,18 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
             const __half2 o = __hsub2(__hmin2(as_h2(r_hi), as_h2(sbx.y)), __hmax2(as_h2(r_lo), as_h2(sbx.x)));
             const bool rok = rvalid & h2_all_ge(as_u32(o), r_wh_t) & h2_all_ge(w.sar[head + s], r_ar);
             const unsigned m = __ballot_sync(0xffffffffu, rok);
-            if (rok) w.item[n_items + __popc(m & lt_mask)] = ((u32)(s * 4 * (int)sizeof(Rec16)) << 16) | (u32)(lane * (int)sizeof(Rec16));
+            if (rok) {
+                const int at = n_items + __popc(m & lt_mask);
+                w.irow[at] = my_row;
+                w.icol[at] = (unsigned short)(s * 4 * (int)sizeof(Rec16));
+            }
             n_items += __popc(m);
         }
     }
-    if (lane < kSlots) w.item[n_items + lane] = (u32)(kTile * (int)sizeof(Rec16));  // pad with the sentinel row (slot 0)
+    if (lane < kSlots) {   // pad with the sentinel row (against slot 0)
+        w.irow[n_items + lane] = (unsigned short)(kTile * (int)sizeof(Rec16));
+        w.icol[n_items + lane] = 0;
+    }
     n_evals += (u32)n_items;
     __syncwarp();
 
@@ -498,26 +529,28 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
     const __half2 zero = as_h2(0u);
     const char* rowbase = reinterpret_cast<const char*>(w.row16);
     const char* colbase = reinterpret_cast<const char*>(w.col16) + j * sizeof(Rec16);
+    const unsigned short* irow = w.irow + grp;
+    const unsigned short* icol = w.icol + grp;
     for (int it = 0; it < n_items; it += kSlots) {
-        const u32 item = w.item[it + grp];
-        const Rec16* rr = reinterpret_cast<const Rec16*>(rowbase + (item & 0xffffu));
-        const Rec16* cc = reinterpret_cast<const Rec16*>(colbase + (item >> 16));
+        const u32 ro = irow[it], co = icol[it];
+        const Rec16* rr = reinterpret_cast<const Rec16*>(rowbase + ro);
+        const Rec16* cc = reinterpret_cast<const Rec16*>(colbase + co);
         const uint4 R = rr->box, C = cc->box;
         const __half2 iw = __hmax2(__hsub2(__hmin2(as_h2(R.z), as_h2(C.z)), __hmax2(as_h2(R.x), as_h2(C.x))), zero);
         const __half2 ih = __hsub2(__hmin2(as_h2(R.w), as_h2(C.w)), __hmax2(as_h2(R.y), as_h2(C.y)));
         const __half2 sum = __hadd2(as_h2(rr->area), as_h2(cc->area));
-        const __half2 x = __hfma2(__hmul2(iw, ih), K, __hneg2(sum));
-        const u32 hit = h2_ge0_bits(as_u32(x));   // bit h: column h of this lane may be an edge (NaN: no overlap at all)
-        if (!__any_sync(0xffffffffu, hit != 0u)) continue;
+        const u32 x = as_u32(__hfma2(__hmul2(iw, ih), K, __hneg2(sum)));
+        if (!__any_sync(0xffffffffu, h2_any_ge0(x))) continue;   // NaN (no overlap at all) is not a candidate
         // queue the candidates (two ballots: first and second column of every lane)
-        const int i = (int)((item & 0xffffu) / (u32)sizeof(Rec16));
-        const int qp = (int)(sub[item >> 23] * kSub) + 2 * j;   // slot = (item >> 16) / 128
-        const bool c0 = (hit & 1u) && i < kTile && qp < M;
-        const bool c1 = (hit & 2u) && i < kTile && qp + 1 < M;
+        const u32 hit = h2_ge0_bits(x);
+        const u32 i = ro / (u32)sizeof(Rec16);
+        const u32 qp = sub[co / (u32)(4 * sizeof(Rec16))] * kSub + 2 * j;
+        const bool c0 = (hit & 1u) && i < kTile;
+        const bool c1 = (hit & 2u) && i < kTile;
         const unsigned m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
-        if (c0) w.cand[n_cand + __popc(m0 & lt_mask)] = ((u32)i << 24) | (u32)qp;
+        if (c0) w.cand[n_cand + __popc(m0 & lt_mask)] = (i << 24) | qp;
         n_cand += __popc(m0);
-        if (c1) w.cand[n_cand + __popc(m1 & lt_mask)] = ((u32)i << 24) | (u32)(qp + 1);
+        if (c1) w.cand[n_cand + __popc(m1 & lt_mask)] = (i << 24) | (qp + 1u);
         n_cand += __popc(m1);
         if (n_cand >= kTile) {
             n_cands += (u32)n_cand;
@@ -533,7 +566,6 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
     EdgeWarp& w = s_w[threadIdx.x >> 5];
     const unsigned lt_mask = (1u << lane) - 1u;
     const u32 total = (u32)a.tcap * (u32)a.B;
-    const float far = 3.0e38f;
 
     for (;;) {
         u32 ticket = 0;
@@ -545,7 +577,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         if (I >= info.n_tiles || info.overflow) continue;
         const int M = info.M;
         const size_t off = (size_t)b * a.cap;
-        const float4* sb = a.sboxes + off;
+        const float4* sb = a.sboxes + (size_t)b * a.scap;
         const u32* srank = a.srank + off;
         const u32* scls = a.scls + off;
         const float4* ts = a.tstat + (size_t)b * a.tcap * 2;
@@ -569,42 +601,37 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         }
         const u32 icmin = __float_as_uint(ia.z), icmax = __float_as_uint(ia.w);
 
-        // ---- this lane's row of tile I: fp32 record for the exact stage, packed record for the filter ----
+        // ---- this lane's row of tile I in the local frame: packed record for the filter, registers for the row tests ----
         const int rp = I * kTile + lane;
         const bool rvalid = rp < M;
-        float4 rq = make_float4(-far, -far, -far, -far);
-        u32 rrank = 0xffffffffu, rcls = 0u;
-        if (rvalid) { rq = sb[rp]; rrank = srank[rp]; rcls = scls[rp]; }
-        u32 r_lo, r_hi, r_wh_t, r_ar;
+        u32 r_lo = 0x63d063d0u, r_hi = 0xe3d0e3d0u, r_wh_t = 0x63d063d0u, r_ar = 0xe3d063d0u;   // +-1000: passes nothing
         __syncwarp();
         {
-            const __half s_lo = __float2half_rz(1000.0f), s_hi = __float2half_rz(-1000.0f);
-            __half x1 = s_lo, y1 = s_lo, x2 = s_hi, y2 = s_hi, ar = __float2half_rz(1.0f);
-            __half wt = s_lo, ht = s_lo, at = s_lo, au = s_hi;
-            if (rvalid) {
-                x1 = __float2half_rd(__fmaf_rd(rq.x, f.S, f.nox));
-                y1 = __float2half_rd(__fmaf_rd(rq.y, f.S, f.noy));
-                x2 = __float2half_ru(__fmaf_ru(rq.z, f.S, f.nox));
-                y2 = __float2half_ru(__fmaf_ru(rq.w, f.S, f.noy));
-                ar = area16_down(rq, f);
-                wt = __float2half_rz(__fmul_rd(__fmul_rd(__fsub_rd(rq.z, rq.x), f.S), t3));
-                ht = __float2half_rz(__fmul_rd(__fmul_rd(__fsub_rd(rq.w, rq.y), f.S), t3));
-                const float up = area_up(rq, f);
-                at = __float2half_rz(__fmul_rd(__fmul_rd(__fmul_rd(__fsub_rd(rq.z, rq.x), __fsub_rd(rq.w, rq.y)), f.S2), t3));
-                au = __hneg(__float2half_ru(up));
-            }
-            r_lo = pack_h2(x1, y1);
-            r_hi = pack_h2(x2, y2);
-            r_wh_t = pack_h2(wt, ht);
-            r_ar = pack_h2(at, au);          // slot {amax up, -(t3*amin) down} >= {t3*area down, -(area up)}
-            w.rowf[lane] = RowF{rq, (rq.z - rq.x) * (rq.w - rq.y), rrank, rcls, 0u};
             Rec16& r16 = w.row16[lane];
-            r16.box = make_uint4(pack_h2(x1, x1), pack_h2(y1, y1), pack_h2(x2, x2), pack_h2(y2, y2));
-            r16.area = pack_h2(ar, ar);
+            uint4 box = make_uint4(0x63d063d0u, 0x63d063d0u, 0xe3d0e3d0u, 0xe3d0e3d0u);
+            u32 area = 0x3c003c00u;
+            if (rvalid) {
+                const float4 rq = sb[rp];
+                const unsigned short x1 = h_dn(__fmaf_rd(rq.x, f.S, f.nox)), y1 = h_dn(__fmaf_rd(rq.y, f.S, f.noy));
+                const unsigned short x2 = h_up(__fmaf_ru(rq.z, f.S, f.nox)), y2 = h_up(__fmaf_ru(rq.w, f.S, f.noy));
+                const unsigned short ar = area16_down(rq, f.S2);
+                const float wd = __fsub_rd(rq.z, rq.x), hd = __fsub_rd(rq.w, rq.y);
+                const unsigned short wt = h_rz(__fmul_rd(__fmul_rd(wd, f.S), t3)), ht = h_rz(__fmul_rd(__fmul_rd(hd, f.S), t3));
+                const unsigned short at = h_rz(__fmul_rd(__fmul_rd(__fmul_rd(wd, hd), f.S2), t3));
+                const unsigned short au = h_up(__fmul_ru(__fmul_ru(__fsub_ru(rq.z, rq.x), __fsub_ru(rq.w, rq.y)), f.S2)) ^ 0x8000u;
+                r_lo = pack2(x1, y1);
+                r_hi = pack2(x2, y2);
+                r_wh_t = pack2(wt, ht);
+                r_ar = pack2(at, au);          // slot {amax up, -(t3*amin) down} >= {t3*area down, -(area up)}
+                box = make_uint4(pack2(x1, x1), pack2(y1, y1), pack2(x2, x2), pack2(y2, y2));
+                area = pack2(ar, ar);
+            }
+            r16.box = box;
+            r16.area = area;
             if (lane == 0) {
                 Rec16& sen = w.row16[kTile];
-                sen.box = make_uint4(pack_h2(s_lo, s_lo), pack_h2(s_lo, s_lo), pack_h2(s_hi, s_hi), pack_h2(s_hi, s_hi));
-                sen.area = pack_h2(__float2half_rz(1.0f), __float2half_rz(1.0f));
+                sen.box = make_uint4(0x63d063d0u, 0x63d063d0u, 0xe3d0e3d0u, 0xe3d0e3d0u);
+                sen.area = 0x3c003c00u;
             }
         }
         __syncwarp();
@@ -670,12 +697,11 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                         const int qi = n_q + __popc(sm & lt_mask);
                         w.sub[qi] = e;
                         // statistics in the local frame, rounded so that the row test can only pass more often
-                        const __half bx1 = __float2half_rd(__fmaf_rd(sbx.x, f.S, f.nox)), by1 = __float2half_rd(__fmaf_rd(sbx.y, f.S, f.noy));
-                        const __half bx2 = __float2half_ru(__fmaf_ru(sbx.z, f.S, f.nox)), by2 = __float2half_ru(__fmaf_ru(sbx.w, f.S, f.noy));
-                        w.sbx[qi] = make_uint2(pack_h2(bx1, by1), pack_h2(bx2, by2));
-                        const __half amax = __float2half_ru(__fmul_ru(__fmul_ru(sar.y, 1.0000077f), f.S2));
-                        const __half amin = __float2half_rz(__fmul_rd(__fmul_rd(__fmul_rd(sar.x, 0.9999923f), f.S2), t3));
-                        w.sar[qi] = pack_h2(amax, __hneg(amin));
+                        w.sbx[qi] = make_uint2(pack2(h_dn(__fmaf_rd(sbx.x, f.S, f.nox)), h_dn(__fmaf_rd(sbx.y, f.S, f.noy))),
+                                               pack2(h_up(__fmaf_ru(sbx.z, f.S, f.nox)), h_up(__fmaf_ru(sbx.w, f.S, f.noy))));
+                        const unsigned short amax = h_up(__fmul_ru(__fmul_ru(sar.y, 1.0000077f), f.S2));
+                        const unsigned short amin = h_rz(__fmul_rd(__fmul_rd(__fmul_rd(sar.x, 0.9999923f), f.S2), t3));
+                        w.sar[qi] = pack2(amax, amin ^ 0x8000u);
                     }
                     n_q += __popc(sm);
                     __syncwarp();
@@ -958,7 +984,7 @@ static GLayout graph_layout(int B, int cap) {
     L.order = o; o = g_align(o + n * 4);
     L.rinv = o; o = g_align(o + n * 4);
     L.pos = o; o = g_align(o + n * 4);
-    L.sboxes = o; o = g_align(o + n * 16);
+    L.sboxes = o; o = g_align(o + (size_t)B * (((size_t)cap + kSub - 1) / kSub * kSub) * 16);
     L.srank = o; o = g_align(o + n * 4);
     L.scls = o; o = g_align(o + n * 4);
     L.tstat = o; o = g_align(o + (size_t)B * tcap * 32);
@@ -981,7 +1007,7 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     char* w = reinterpret_cast<char*>(ws);
     GArgs a;
     a.boxes = reinterpret_cast<const float4*>(boxes); a.scores = scores; a.classes = classes; a.counts = counts;
-    a.B = B; a.cap = cap; a.tcap = (cap + kTile - 1) / kTile;
+    a.B = B; a.cap = cap; a.tcap = (cap + kTile - 1) / kTile; a.scap = (cap + kSub - 1) / kSub * kSub;
     a.thr = (float)iou_threshold;
     a.thr_fast_ok = (a.thr >= 0.03f && a.thr <= 1e30f) ? 1 : 0;
     a.t3 = a.thr * (1.0f - 0.015625f);
