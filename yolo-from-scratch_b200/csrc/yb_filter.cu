@@ -6,15 +6,19 @@
 // plus M*row_bytes for the rows that pass and 28*M for the candidate list.
 // A tile is 128 consecutive rows of one scale of one image; a CTA owns a GROUP of G consecutive
 // tiles (G = 1 for 85-float rows, 8 for 6-float rows: ~24-44 KB of head data per CTA), so that
-// every thread has G independent loads in flight.  Two launches:
-//   filter_count_kernel  objectness test, pass count per tile
-//   filter_emit_kernel   per-image exclusive prefix over the tile counts (order preserving),
-//                        in-tile ballot scan, and for the passing rows decode + class max +
-//                        box build.  Dense groups are staged in shared memory by ONE bulk-async
-//                        copy (cp.async.bulk, mbarrier completion): the rows of a group are
-//                        contiguous in the head tensor, so the whole group is a single 1-D TMA
-//                        transfer and several CTAs per SM keep >100 KB in flight.  Rows are
-//                        then read at stride 5+nc words (odd for nc=80: conflict-free).
+// every thread has G independent loads in flight.  ONE launch (round 2; round 1 read the objectness column
+// twice, in a count kernel and again in an emit kernel):
+//   filter_onepass_kernel  objectness test of the group (strided 4-byte loads: every line of a 24-byte-row
+//                        head, one 128-byte line per 340-byte row), pass counts per tile, then a DECOUPLED
+//                        LOOK-BACK over the groups of the image (order preserving: a group publishes its
+//                        count, then its inclusive prefix, in one 64-bit word; successors add up what they
+//                        find behind them; group ids are handed out by a per-image ticket so that every
+//                        predecessor is already running), in-tile ballot scan, and for the passing rows
+//                        decode + class max + box build.  Dense groups are staged in shared memory by ONE
+//                        bulk-async copy (cp.async.bulk, mbarrier completion) that is in flight while the
+//                        look-back waits: the rows of a group are contiguous in the head tensor, so the
+//                        whole group is a single 1-D TMA transfer.  Rows are then read at stride 5+nc words
+//                        (odd for nc=80: conflict-free).  The heads cross the HBM interface once.
 #include "yb_common.cuh"
 
 namespace yb {
@@ -37,11 +41,14 @@ struct FilterArgs {
     int S, A, nc, cap, G, nchw;
     uint32_t row, tiles_per_img, groups_per_img;
     float img, inv_img, conf;
+    float obj_lo, obj_hi;      // logits clearly below / above logit(conf): sigmoid(x) > conf decided without the sigmoid
     int stage_ok;              // shared-memory staging available for this row length
     uint32_t sobj_offset;      // float offset of the sigmoid(obj) scratch in dynamic shared memory
     const float* letterbox;    // (B,3) scale, pad_top, pad_left or null
     FilterScale sc[YB_MAX_SCALES];
-    int* tile_counts;          // (B, tiles_per_img)
+    int* tile_counts;          // (B, tiles_per_img)      (NCHW two-launch path)
+    unsigned long long* lb_state;  // (B, groups_per_img): flag << 32 | value, zeroed before the launch
+    unsigned int* lb_ticket;       // (B): next group id of every image
     float4* boxes;
     float* scores;
     int64_t* classes;
@@ -69,31 +76,6 @@ __device__ __forceinline__ int group_scale(const FilterArgs& a, uint32_t group) 
     for (int k = 1; k < YB_MAX_SCALES; ++k)
         if (k < a.S && group >= a.sc[k].group_begin) s = k;
     return s;
-}
-
-__global__ void __launch_bounds__(kFTile) filter_count_kernel(const FilterArgs a) {
-    const uint32_t group = blockIdx.x, b = blockIdx.y;
-    const FilterScale& L = a.sc[group_scale(a, group)];
-    const uint32_t tile0 = (group - L.group_begin) * a.G;        // tile within the scale
-    const uint32_t ntiles = (L.rows + kFTile - 1) / kFTile;
-    float x[kFMaxGroup];
-#pragma unroll
-    for (int k = 0; k < kFMaxGroup; ++k) {
-        const uint32_t r = (tile0 + k) * kFTile + threadIdx.x;
-        x[k] = -INFINITY;
-        if (k < a.G && r < L.rows) {
-            uint32_t cs;
-            const size_t base = frow_base(a, L, b, r, cs);
-            x[k] = __ldg(L.pred + base + 4 * (size_t)cs);  // objectness
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kFMaxGroup; ++k) {
-        if (k >= a.G || tile0 + k >= ntiles) break;  // uniform
-        const bool pass = sigmoidf_ref(x[k]) > a.conf;  // :1157,:1166-1167 objectness only
-        const int n = __syncthreads_count(pass);
-        if (threadIdx.x == 0) a.tile_counts[b * a.tiles_per_img + L.tile_begin + tile0 + k] = n;
-    }
 }
 
 // first index of the maximum of sigmoid(x[0..nc)) — torch.max(dim=1) semantics (:1189).
@@ -125,6 +107,7 @@ __device__ __forceinline__ void class_max(int nc, Load ld, float& prob, int& id)
     for (; c < nc; ++c) step(ld(c), c);
     prob = sigmoidf_ref(m);
     id = mi;
+    if (m <= 5.0f && !(m2 > m - 3.1e-4f)) return;  // 2e-6*(1+e^5) < 3.1e-4: the common case without the exponential
     const float lo = (m <= 14.0f) ? m - 2e-6f * (1.0f + expf(m)) : 13.0f;
     if (!(m2 > lo)) return;  // nothing else is close enough to round to the same probability
     for (c = 0; c < nc; ++c) {  // near-ties on either side of mi (expf need not be monotone to the last ulp)
@@ -162,59 +145,77 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
-__global__ void __launch_bounds__(kFTile) filter_emit_kernel(const FilterArgs a) {
+// ---- decoupled look-back over the groups of one image -------------------------------------------------------
+// state word: flag << 32 | value; flag 1 = value is the group's own count, 2 = value is the inclusive prefix.
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Exclusive prefix of group g (one full warp calls this; st = the image's state row; the group's own count has
+// been published already).  Lane l inspects predecessor g-1-l of the current window of 32.
+__device__ __forceinline__ int lb_exclusive(const unsigned long long* st, int g, int lane) {
+    int prefix = 0;
+    for (int hi = g - 1; hi >= 0; hi -= 32) {
+        const int k = hi - lane;
+        unsigned long long v = 3ull << 32;   // beyond the first group: behaves like an inclusive prefix of 0
+        for (;;) {
+            if (k >= 0) v = lb_load(st + k);
+            const unsigned ready = __ballot_sync(0xffffffffu, (v >> 32) != 0ull);
+            const unsigned incl = __ballot_sync(0xffffffffu, (v >> 32) >= 2ull);
+            // the nearest predecessor that already knows its inclusive prefix ends the walk; everything nearer
+            // must at least have published its count
+            const int stop = incl ? __ffs(incl) - 1 : 32;
+            const unsigned need = stop >= 32 ? 0xffffffffu : ((2u << stop) - 1u);
+            if ((ready & need) == need) {
+                int part = (lane <= stop && k >= 0) ? (int)(unsigned)(v & 0xffffffffull) : 0;
+                part = __reduce_add_sync(0xffffffffu, part);
+                prefix += part;
+                if (stop < 32) return prefix;
+                break;
+            }
+        }
+    }
+    return prefix;
+}
+
+__global__ void __launch_bounds__(kFTile) filter_onepass_kernel(const FilterArgs a) {
     extern __shared__ __align__(128) float s_tile[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_red[kFTile / 32];
     __shared__ int s_wcnt[kFMaxGroup][kFTile / 32];
-    __shared__ unsigned s_bal[kFMaxGroup][kFTile / 32];
-    __shared__ int s_cnt[kFMaxGroup];
-    // sigmoid(obj) of this thread's row in every tile of the group lives behind the staged rows
-    float(*s_sobj)[kFTile] = reinterpret_cast<float(*)[kFTile]>(s_tile + a.sobj_offset);
-    const uint32_t group = blockIdx.x, b = blockIdx.y;
+    __shared__ int s_prefix, s_total;
+    __shared__ unsigned s_gid;
+    // row ids (within the group) of the passing rows, in row order, live behind the staged rows
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_tile + a.sobj_offset);
+    const uint32_t b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        s_gid = atomicAdd(a.lb_ticket + b, 1u);   // the g-th CTA of the image to start owns group g
+    }
+    __syncthreads();
+    const uint32_t group = s_gid;
     const int s = group_scale(a, group);
     const FilterScale& L = a.sc[s];
     const uint32_t tile0 = (group - L.group_begin) * a.G;  // within the scale
     const uint32_t ntiles = (L.rows + kFTile - 1) / kFTile;
     const int G = (int)min((uint32_t)a.G, ntiles - tile0);  // tiles of this group
-    const uint32_t first_tile = L.tile_begin + tile0;       // within the image
-    const int* tc = a.tile_counts + b * a.tiles_per_img;
-
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-
-    // exclusive prefix of this group within its image, and the group's own counts
-    int part = 0;
-    for (uint32_t t = threadIdx.x; t < first_tile; t += kFTile) part += tc[t];
-    part = __reduce_add_sync(0xffffffffu, part);
-    if (lane == 0) s_red[warp] = part;
-    __syncthreads();
-    int prefix = 0;
-#pragma unroll
-    for (int k = 0; k < kFTile / 32; ++k) prefix += s_red[k];
-    int total = 0;
-#pragma unroll
-    for (int k = 0; k < kFMaxGroup; ++k) {
-        const int c = k < G ? tc[first_tile + k] : 0;
-        if (threadIdx.x == 0) s_cnt[k] = c;
-        total += c;
-    }
-    if (first_tile + G == a.tiles_per_img && threadIdx.x == 0) {
-        const int tot = prefix + total;
-        a.counts[b] = tot < a.cap ? tot : a.cap;
-    }
-    if (total == 0) return;
-
     const uint32_t row0 = tile0 * kFTile;
     const uint32_t nrows = min((uint32_t)(G * kFTile), L.rows - row0);
     const size_t base = ((size_t)b * L.rows + row0) * a.row;  // float offset of the group
     const float* g = L.pred + base;
+    unsigned long long* st = a.lb_state + (size_t)b * a.groups_per_img;
 
-    // dense groups: stage through shared memory
-    const bool staged = a.stage_ok && !a.nchw && total * 4 >= (int)nrows;
-    if (staged) {
-        const uint32_t nfl = nrows * a.row;
-        if ((base & 3) == 0 && (nfl & 3) == 0) {
+    // rows of at most 32 bytes: the objectness column touches every sector anyway, so the whole group is staged
+    // up front (one bulk copy issued before anything else) and phase A reads shared memory
+    const uint32_t nfl = nrows * a.row;
+    const bool can_bulk = (base & 3) == 0 && (nfl & 3) == 0;
+    const bool early = a.stage_ok && a.row <= 8;
+    if (early) {
+        if (can_bulk) {
             if (threadIdx.x == 0) bulk_load(s_tile, g, nfl * 4u, &s_bar);
             mbar_wait(&s_bar, 0);
         } else {
@@ -223,58 +224,105 @@ __global__ void __launch_bounds__(kFTile) filter_emit_kernel(const FilterArgs a)
         }
     }
 
-    // phase A: objectness test of this thread's row in every tile of the group
-#pragma unroll 2
-    for (int k = 0; k < G; ++k) {
+    // phase A: objectness test of this thread's row in every tile of the group (the only pass over the column).
+    // sigmoid(x) > conf is decided from the logit when x is clearly on one side of logit(conf) (the fp32
+    // sigmoid is within a few ulp of the real one, so a margin of obj_margin in x cannot flip the comparison);
+    // rows inside the margin evaluate the reference expression.
+    float xo[kFMaxGroup];
+#pragma unroll
+    for (int k = 0; k < kFMaxGroup; ++k) {
         const uint32_t rl = k * kFTile + threadIdx.x;
-        bool pass = false;
-        float so = 0.0f;
-        if (rl < nrows) {
-            uint32_t cs;
-            const size_t rb = frow_base(a, L, b, row0 + rl, cs);
-            const float xo = staged ? s_tile[rl * a.row + 4] : __ldg(L.pred + rb + 4 * (size_t)cs);
-            so = sigmoidf_ref(xo);
-            pass = so > a.conf;
+        xo[k] = __int_as_float(0x7fc00000);   // NaN: fails both quick tests and the exact one
+        if (k < G && rl < nrows) xo[k] = early ? s_tile[rl * a.row + 4] : __ldg(g + (size_t)rl * a.row + 4);
+    }
+    unsigned mybal[kFMaxGroup];
+#pragma unroll
+    for (int k = 0; k < kFMaxGroup; ++k) {
+        mybal[k] = 0u;
+        if (k < G) {
+            bool pass = xo[k] > a.obj_hi;
+            if (!pass && xo[k] > a.obj_lo) pass = sigmoidf_ref(xo[k]) > a.conf;   // :1157,:1166-1167 objectness only
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            mybal[k] = bal;
+            if (lane == 0) s_wcnt[k][warp] = __popc(bal);
         }
-        s_sobj[k][threadIdx.x] = so;
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (lane == 0) { s_wcnt[k][warp] = __popc(bal); s_bal[k][warp] = bal; }
     }
     __syncthreads();
+    // offsets of this warp's rows of tile k in the group's list; the group's total
+    int woff[kFMaxGroup];
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < kFMaxGroup; ++k) {
+        woff[k] = total;
+        if (k < G) {
+#pragma unroll
+            for (int w = 0; w < kFTile / 32; ++w) {
+                const int c = s_wcnt[k][w];
+                if (w < warp) woff[k] += c;
+                total += c;
+            }
+        }
+    }
+    // publish the group's count (the first group's count is its inclusive prefix)
+    if (threadIdx.x == 0) lb_store(st + group, ((group == 0 ? 2ull : 1ull) << 32) | (unsigned)total);
 
-    // phase B: emit
+    // dense groups: stage through shared memory while the look-back is in progress
+    const bool staged = early || (a.stage_ok && total * 4 >= (int)nrows);
+    bool bulk = false;
+    if (staged && !early) {
+        bulk = can_bulk;
+        if (bulk) {
+            if (threadIdx.x == 0) bulk_load(s_tile, g, nfl * 4u, &s_bar);
+        } else {
+            for (uint32_t e = threadIdx.x; e < nfl; e += kFTile) s_tile[e] = g[e];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kFMaxGroup; ++k)
+        if (k < G && ((mybal[k] >> lane) & 1u))
+            s_list[woff[k] + __popc(mybal[k] & ((1u << lane) - 1u))] = (unsigned short)(k * kFTile + threadIdx.x);
+    if (warp == 0) {
+        const int p = group == 0 ? 0 : lb_exclusive(st, (int)group, lane);
+        if (lane == 0) {
+            s_prefix = p;
+            if (group != 0) lb_store(st + group, (2ull << 32) | (unsigned)(p + total));
+            if (group + 1 == a.groups_per_img) {
+                const int tot = p + total;
+                a.counts[b] = tot < a.cap ? tot : a.cap;
+            }
+        }
+    }
+    __syncthreads();
+    if (total == 0) return;
+    const int prefix = s_prefix;
+    if (bulk) mbar_wait(&s_bar, 0);
+
+    // phase B: emit, one passing row per thread and step (the list is dense: no idle lanes at any pass rate)
     float inv_s = 1.0f, pt = 0.0f, pl = 0.0f;
     if (a.letterbox) {
         inv_s = 1.0f / a.letterbox[b * 3 + 0];
         pt = a.letterbox[b * 3 + 1];
         pl = a.letterbox[b * 3 + 2];
     }
+    const int n_emit = min(total, a.cap - prefix);
 #pragma unroll 1
-    for (int k = 0; k < G; ++k) {
-        const unsigned bal = s_bal[k][warp];
-        const bool pass = (bal >> lane) & 1u;
-        int pos = prefix + __popc(bal & ((1u << lane) - 1));
-        for (int w = 0; w < warp; ++w) pos += s_wcnt[k][w];
-        prefix += s_cnt[k];
-        if (!pass || pos >= a.cap) continue;
-        const uint32_t rl = k * kFTile + threadIdx.x;
+    for (int c = threadIdx.x; c < n_emit; c += kFTile) {
+        const uint32_t rl = s_list[c];
         const uint32_t r = row0 + rl;
         uint32_t cell, an, gy, gx;
         L.d_A.divmod(r, cell, an);
         L.d_W.divmod(cell, gy, gx);
         const float aw = __ldg(L.anchors + an * 2), ah = __ldg(L.anchors + an * 2 + 1);
-        float x0, x1r, x2r, x3r, cprob;
+        float x0, x1r, x2r, x3r, x4r, cprob;
         int cid;
         if (staged) {
             const float* x = s_tile + rl * a.row;
-            x0 = x[0]; x1r = x[1]; x2r = x[2]; x3r = x[3];
-            class_max(a.nc, [&](int c) { return x[5 + c]; }, cprob, cid);
+            x0 = x[0]; x1r = x[1]; x2r = x[2]; x3r = x[3]; x4r = x[4];
+            class_max(a.nc, [&](int cc) { return x[5 + cc]; }, cprob, cid);
         } else {
-            uint32_t cs;
-            const float* x = L.pred + frow_base(a, L, b, r, cs);
-            const size_t st = cs;
-            x0 = __ldg(x); x1r = __ldg(x + st); x2r = __ldg(x + 2 * st); x3r = __ldg(x + 3 * st);
-            class_max(a.nc, [&](int c) { return __ldg(x + (size_t)(5 + c) * st); }, cprob, cid);
+            const float* x = g + (size_t)rl * a.row;
+            x0 = __ldg(x); x1r = __ldg(x + 1); x2r = __ldg(x + 2); x3r = __ldg(x + 3); x4r = __ldg(x + 4);
+            class_max(a.nc, [&](int cc) { return __ldg(x + 5 + cc); }, cprob, cid);
         }
         // decode (:1154) with the model's img_size
         const float bx = decode_xy(x0, (float)gx, L.inv_w);
@@ -288,9 +336,9 @@ __global__ void __launch_bounds__(kFTile) filter_emit_kernel(const FilterArgs a)
             x1 = (x1 - pl) * inv_s; y1 = (y1 - pt) * inv_s;
             x2 = (x2 - pl) * inv_s; y2 = (y2 - pt) * inv_s;
         }
-        const size_t o = (size_t)b * a.cap + pos;
+        const size_t o = (size_t)b * a.cap + prefix + c;
         a.boxes[o] = make_float4(x1, y1, x2, y2);
-        a.scores[o] = s_sobj[k][threadIdx.x] * cprob;  // :1216
+        a.scores[o] = sigmoidf_ref(x4r) * cprob;  // :1216
         a.classes[o] = (int64_t)cid;
     }
 }
@@ -475,7 +523,10 @@ static int filter_fill(const yb_heads_desc* d, FilterArgs& a) {
 extern "C" size_t yb_filter_workspace_bytes(const yb_heads_desc* d) {
     yb::FilterArgs a;
     if (yb::filter_fill(d, a)) return 0;
-    return (size_t)d->B * a.tiles_per_img * sizeof(int) + 16;
+    // NCHW: per-tile counts (4 B); reference layout: look-back state (8 B per group) + one ticket per image
+    const size_t nchw = (size_t)d->B * a.tiles_per_img * sizeof(int);
+    const size_t lb = (size_t)d->B * a.groups_per_img * sizeof(unsigned long long) + (size_t)d->B * sizeof(unsigned int);
+    return (nchw > lb ? nchw : lb) + 16;
 }
 
 extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const float* letterbox,
@@ -487,7 +538,7 @@ extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const
     if (rc) return rc;
     if (d->B == 0) return 0;
     YB_CHECK_ARG(boxes && scores && classes && counts && ws && cap > 0, "filter: null output");
-    YB_CHECK_ARG(aligned16(boxes), "filter: boxes must be 16-byte aligned");
+    YB_CHECK_ARG(aligned16(boxes) && (reinterpret_cast<uintptr_t>(ws) & 7u) == 0, "filter: boxes must be 16-byte, the workspace 8-byte aligned");
     for (int s = 0; s < d->S; ++s)
         YB_CHECK_ARG(d->pred[s] && d->anchors[s] && aligned16(d->pred[s]), "filter: bad tensor at scale %d", s);
     if (ws_bytes < yb_filter_workspace_bytes(d)) {
@@ -496,6 +547,18 @@ extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const
     }
     YB_CHECK_ARG(d->B <= 65535, "filter: B too large");
     a.cap = cap; a.conf = conf_thres; a.letterbox = letterbox;
+    {
+        // sigmoid(x) > conf  <=>  x > logit(conf) in real arithmetic; 1/(1+expf(-x)) is within 4 ulp of it, i.e.
+        // within 2^-21 relative, which moves the crossing point by at most 2^-21/(1-s) (s > 1/2) or 2^-21/s in x.
+        // A margin 64x that wide is used; thresholds too close to 0 or 1 always take the exact expression.
+        const double c = (double)conf_thres;
+        a.obj_lo = -INFINITY; a.obj_hi = INFINITY;
+        if (c > 1e-4 && c < 1.0 - 1e-4) {
+            const double lg = log(c / (1.0 - c));
+            const double m = 64.0 * 4.8e-7 / (c < 0.5 ? c : 1.0 - c) + 1e-5 * fabs(lg) + 1e-6;
+            a.obj_lo = (float)(lg - m); a.obj_hi = (float)(lg + m);
+        }
+    }
     a.tile_counts = reinterpret_cast<int*>(ws);
     a.boxes = reinterpret_cast<float4*>(boxes); a.scores = scores; a.classes = classes; a.counts = counts;
     size_t smem = (size_t)a.G * kFTile * a.row * sizeof(float);
@@ -503,7 +566,7 @@ extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const
     if (!a.stage_ok) smem = 0;
     smem = (smem + 15) / 16 * 16;
     a.sobj_offset = (uint32_t)(smem / sizeof(float));
-    smem += (size_t)a.G * kFTile * sizeof(float);
+    smem += (size_t)a.G * kFTile * sizeof(float);   // NCHW: sigmoid(obj) scratch; reference layout: u16 row list (half of it)
     cudaStream_t st = (cudaStream_t)stream;
     if (a.nchw) {
         FilterNchw n;
@@ -519,10 +582,12 @@ extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const
         return 0;
     }
     dim3 grid(a.groups_per_img, d->B);
-    YB_LAUNCH("filter_count_kernel", st, filter_count_kernel<<<grid, kFTile, 0, st>>>(a));
+    a.lb_state = reinterpret_cast<unsigned long long*>(ws);
+    a.lb_ticket = reinterpret_cast<unsigned int*>(a.lb_state + (size_t)d->B * a.groups_per_img);
+    YB_CUDA(cudaMemsetAsync(ws, 0, (size_t)d->B * a.groups_per_img * sizeof(unsigned long long) + (size_t)d->B * sizeof(unsigned int), st));
     const size_t dyn = smem;
     if (dyn > 48 * 1024)
-        YB_CUDA(cudaFuncSetAttribute(filter_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    YB_LAUNCH("filter_emit_kernel", st, filter_emit_kernel<<<grid, kFTile, dyn, st>>>(a));
+        YB_CUDA(cudaFuncSetAttribute(filter_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    YB_LAUNCH("filter_onepass_kernel", st, filter_onepass_kernel<<<grid, kFTile, dyn, st>>>(a));
     return 0;
 }
