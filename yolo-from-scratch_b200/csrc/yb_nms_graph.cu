@@ -12,11 +12,13 @@
 //      result is the unique fixed point of  "kept <=> every higher-scored neighbour is
 //      suppressed; suppressed <=> some higher-scored neighbour is kept", reached by parallel
 //      rounds (8 rounds on 25,200 random boxes).
-// Four launches for a whole batch:
-//   graph_sort_kernel     two CTAs per image: stable score order (rank <-> index maps) and spatial
-//                         order, each by a shared-memory blocked radix sort (yb_sort.cuh)
-//   graph_gather_kernel   boxes / rank / class in position order (coordinate-offset trick applied),
-//                         bounding statistics per 32-box tile and per 8-box sub-tile
+// Five launches for a whole batch:
+//   graph_score_kernel    one CTA per image: stable score order (rank <-> index maps), shared-memory blocked
+//                         radix sort (yb_sort.cuh); on a side stream, needed by the resolve kernel only
+//   graph_spatial_kernel  one CTA per chunk of 26,880 candidates: 14-bit spatial key (class | area bucket |
+//                         Hilbert index), one counting pass in shared memory -> position order
+//   graph_gather_kernel   boxes / score keys / indices / classes in position order (coordinate-offset trick
+//                         applied), bounding statistics per 32-box tile and per 8-box sub-tile (REDUX)
 //   graph_edge_kernel     persistent warps, one row tile at a time, three culling levels (tile,
 //                         sub-tile, row vs sub-tile), surviving (row, sub-tile) items packed so that
 //                         every pair-loop iteration tests 4 items x 8 columns on all 32 lanes;
@@ -29,6 +31,8 @@
 #include "yb_common.cuh"
 #include "yb_sort.cuh"
 #include <cuda_fp16.h>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 namespace yb {
@@ -65,13 +69,16 @@ struct GArgs {
     u32 k16x2;      // half2 {K, K}, K = (1+th)/th * (1+2^-6) rounded up, th = thr * (1 - 2^-12)
     int hexp;       // local frames map a row tile's half extent to [2^hexp, 2^(hexp+1))
     long long trick_max_numel;
-    u32 *k0, *v0, *k1, *v1, *k2, *v2;  // (B,cap) radix ping-pong buffers
-    u32* order;                        // (B,cap) score rank -> original index      (score CTA)
-    u32* rinv;                         // (B,cap) original index -> score rank      (score CTA)
-    u32* pos;                          // (B,cap) position -> original index        (spatial CTA)
-    float4* sboxes;                    // (B,cap) boxes in position order (offset applied)
-    u32* srank;                        // (B,cap) position -> score rank
+    u32 *k0, *v0, *k1, *v1;            // (B,cap) radix ping-pong buffers (ballot score sort of large images only)
+    u32* order;                        // (B,cap) score rank -> original index      (score kernel)
+    u32* rinv;                         // (B,cap) original index -> score rank      (score kernel)
+    u32* pos;                          // (B,cap) position -> original index        (spatial kernel)
+    float4* sboxes;                    // (B,scap) boxes in position order (offset applied)
+    u32* skey;                         // (B,cap) position -> descending-score key (ties: lower original index first)
+    u32* sidx;                         // (B,cap) position -> original index
     u32* scls;                         // (B,cap) position -> class id (per-class mode)
+    int* iflags;                       // (B) per-image flags ORed by the chunks of the spatial kernel (zeroed per call)
+    int n_chunks;                      // spatial chunks per image
     float4* tstat;                     // (B,tcap,2) tile bbox | {amin, amax, cmin, cmax}
     float4* sstat;                     // (B,tcap,kSubs,2) sub-tile bbox | {amin, amax, -, -}
     GImg* info;
@@ -81,13 +88,6 @@ struct GArgs {
     int64_t* keep;
     int* n_keep;
 };
-
-__device__ __forceinline__ u32 spread8(u32 v) {  // 8 bits -> even bit positions of 16
-    v = (v | (v << 4)) & 0x0f0fu;
-    v = (v | (v << 2)) & 0x3333u;
-    v = (v | (v << 1)) & 0x5555u;
-    return v;
-}
 
 template <int NT>
 __device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float* s32, int lane, int warp) {
@@ -106,98 +106,159 @@ __device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float
 
 // Hilbert index of an 8-bit cell (x, y): a CONTINUOUS space-filling curve, so 32 consecutive boxes never jump
 // across the image the way the Z-order's quadrant changes make them (those tiles had bounding boxes spanning
-// half the image and did 3x the average work).
-__device__ __forceinline__ u32 hilbert8(u32 x, u32 y) {
-    u32 d = 0;
+// half the image and did 3x the average work).  Evaluated a nibble at a time through a 4-state table
+// (state = complement | swap << 1 of the remaining low bits) built in shared memory at kernel start:
+// two lookups instead of an 8-level bit loop of ~80 instructions per box.
+__device__ __forceinline__ unsigned short hilbert_lut_entry(int state, u32 x, u32 y) {   // x, y: 4-bit
+    if (state & 1) { x = 15u - x; y = 15u - y; }
+    if (state & 2) { const u32 t = x; x = y; y = t; }
+    u32 d = 0, c = 0, sw = 0;
 #pragma unroll
-    for (u32 s = 128u; s > 0u; s >>= 1) {
+    for (u32 s = 8u; s > 0u; s >>= 1) {
         const u32 rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
         d += s * s * ((3u * rx) ^ ry);
         if (ry == 0u) {
-            if (rx == 1u) { x = 255u - x; y = 255u - y; }
+            if (rx == 1u) { x = 15u - x; y = 15u - y; c ^= 1u; }
             const u32 t = x; x = y; y = t;
+            sw ^= 1u;
         }
     }
-    return d;
+    return (unsigned short)(d | ((((u32)state & 1u) ^ c) << 8) | (((((u32)state >> 1) & 1u) ^ sw) << 9));
+}
+__device__ __forceinline__ u32 hilbert8(const unsigned short* lut, u32 x, u32 y) {   // lut[state*256 + xn*16 + yn]
+    const u32 e = lut[((x >> 4) << 4) | (y >> 4)];
+    const u32 e2 = lut[((e >> 8) << 8) | ((x & 15u) << 4) | (y & 15u)];
+    return ((e & 255u) << 8) | (e2 & 255u);
 }
 
-// spatial sort key: (class | area bucket of 1.5 octaves | Hilbert index of the centre, direction alternating
-// with the bucket's parity so that a tile straddling two buckets stays in one corner of the image).
-// tools/nms_cull_sim.py on the bench workload, per image: sub-tile pairs 30.3 K -> 17.9 K, (row, sub-tile)
-// items 161 K -> 119 K, heaviest row tile 842 -> 160 sub-tile pairs, against the round-1 key (2-octave bucket,
-// Z-order).
-__device__ __forceinline__ u32 spatial_key(const float4 q, const int64_t* classes, int i, float cmin, float qs) {
+// area bucket of 1.5 octaves (tools/nms_cull_sim.py: fewest sub-tile pairs on the bench workload)
+__device__ __forceinline__ u32 area_bucket(const float4 q) {
     const float area = (q.z - q.x) * (q.w - q.y);
     const float lg = fminf(fmaxf(__log2f(area), -44.0f), 120.0f);   // area <= 0 or NaN -> lowest bucket
-    const u32 bucket = (u32)(int)floorf(lg * 0.6666667f + 32.0f) & 0x7fu;
-    const float fx = fminf(fmaxf(((q.x + q.z) * 0.5f - cmin) * qs, 0.0f), 255.0f);
-    const float fy = fminf(fmaxf(((q.y + q.w) * 0.5f - cmin) * qs, 0.0f), 255.0f);
-    u32 curve = hilbert8((u32)fx, (u32)fy);
+    return (u32)(int)floorf(lg * 0.6666667f + 32.0f) & 0x7fu;
+}
+
+// 14-bit spatial key: class | area bucket (relative to the chunk's lowest) | Hilbert index of the centre, the
+// curve's direction alternating with the bucket's parity so that a tile straddling two buckets stays in one corner
+// of the image.  The field widths are chosen per chunk (KeyBits).  The order only has to be spatially coherent:
+// tools/nms_cull_sim.py shows no loss down to 9 curve bits even with a random order inside a key, so the sort is ONE
+// counting pass with shared-memory atomics.  Against round 1's (2-octave bucket | Z-order), per image of the bench
+// workload: sub-tile pairs 30.3 K -> 18 K, (row, sub-tile) items 161 K -> 120 K, heaviest row tile 842 -> 160.
+constexpr int kKeyBits = 14;
+struct KeyBits {
+    int cls_shift, bkt_shift, bkt_drop, curve_drop;
+    u32 bmin;
+    float cmin, qs;
+};
+__device__ __forceinline__ u32 spatial_key(const float4 q, const int64_t* classes, int i, const KeyBits& kb,
+                                           const unsigned short* lut) {
+    const u32 bucket = area_bucket(q);
+    const float fx = fminf(fmaxf(((q.x + q.z) * 0.5f - kb.cmin) * kb.qs, 0.0f), 255.0f);
+    const float fy = fminf(fmaxf(((q.y + q.w) * 0.5f - kb.cmin) * kb.qs, 0.0f), 255.0f);
+    u32 curve = hilbert8(lut, (u32)fx, (u32)fy);
     if (bucket & 1u) curve ^= 0xffffu;
     const u32 c = classes ? ((u32)classes[i] & 0x1ffu) : 0u;
-    return (c << 23) | (bucket << 16) | curve;
+    return ((c << kb.cls_shift) | (((bucket - kb.bmin) >> kb.bkt_drop) << kb.bkt_shift) | (curve >> kb.curve_drop)) &
+           ((1u << kKeyBits) - 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
-// sort: two independent CTAs per image (blockIdx.y = 0: score order, 1: spatial order).
-// SMEM = true: shared-memory blocked sort (cap <= kS16MaxM, 512 threads); false: warp-ballot sort
-// through global ping-pong buffers (any cap, 1024 threads).
+// score order: stable descending sort of one image, rank <-> index maps.  Its own launch on a side stream:
+// only the resolve kernel needs it, so it overlaps with the spatial kernel and the edge discovery.
+// SMEM = true: shared-memory blocked sort (cap <= kS16MaxM, 512 threads); false: warp-ballot sort through
+// global ping-pong buffers (any cap, 1024 threads).
 // ------------------------------------------------------------------------------------------------
 template <int NT, bool SMEM>
-__global__ void __launch_bounds__(NT) graph_sort_kernel(const GArgs a) {
+__global__ void __launch_bounds__(NT) graph_score_kernel(const GArgs a) {
     extern __shared__ __align__(16) u32 s_dyn[];  // SMEM: s16_smem_bytes(cap); else 32*256 + 256 words
+    __shared__ int s_skip;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const size_t off = (size_t)b * a.cap;
+    int M = a.counts ? a.counts[b] : a.cap;
+    M = M < 0 ? 0 : (M > a.cap ? a.cap : M);
+    if (M == 0) return;
+    const float* scores = a.scores + off;
+    u32* order = a.order + off;
+    u32* rinv = a.rinv + off;
+    if (SMEM) {
+        const u32* res = s16_sort(M, a.cap, [&](int i) { return desc_key(scores[i]); }, s_dyn);
+        for (int r = tid; r < M; r += NT) {
+            const u32 idx = res[r] >> 16;
+            order[r] = idx;
+            rinv[idx] = (u32)r;
+        }
+    } else {
+        u32 *ka = a.k0 + off, *va = a.v0 + off, *kb = a.k1 + off, *vb = a.v1 + off;
+        for (int i = tid; i < M; i += NT) { ka[i] = desc_key(scores[i]); va[i] = (u32)i; }
+        __syncthreads();
+        radix_sort(ka, va, kb, vb, M, 0, 32, s_dyn, s_dyn + 32 * 256, &s_skip);
+        for (int r = tid; r < M; r += NT) {
+            const u32 idx = va[r];
+            order[r] = idx;
+            rinv[idx] = (u32)r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// spatial order + gather.  One CTA of 1024 threads per chunk of kChunk candidates of one image (one chunk at
+// 640^2; a 1280^2 image is four chunks = horizontal bands of the P3 grid, because candidates arrive in row-major
+// grid order): validity / range reductions, 14-bit spatial key, ONE counting pass (histogram and scatter with
+// shared-memory atomics; the order inside a key is arbitrary and changes nothing but the work distribution), then
+// — straight from shared memory — boxes (coordinate-offset trick applied, boxes.py:99-101), score keys, original
+// indices and classes in position order, and the bounding statistics of every 32-box tile and 8-box sub-tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kChunk = 26880;        // 840 tiles; u16 indices
+constexpr int kSpThreads = 1024;
+
+__host__ __device__ inline size_t spatial_smem_bytes(int ccap) {
+    return ((size_t)1 << kKeyBits) * sizeof(u32) + 2 * (((size_t)ccap + 7) / 8 * 8) * sizeof(unsigned short) +
+           1024 * sizeof(unsigned short);
+}
+
+__global__ void __launch_bounds__(kSpThreads) graph_spatial_kernel(const GArgs a) {
+    extern __shared__ __align__(16) u32 s_dyn[];
     __shared__ float s_f[32];
     __shared__ int s_flag[32];
     __shared__ int s_maxcls[32];
-    __shared__ int s_skip;
+    __shared__ int s_bmin[32], s_bmax[32];
+    __shared__ u32 s_scan[32];
+    constexpr int NT = kSpThreads;
+    constexpr int NB = 1 << kKeyBits;
 
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t off = (size_t)b * a.cap;
     int M = a.counts ? a.counts[b] : a.cap;
     M = M < 0 ? 0 : (M > a.cap ? a.cap : M);
     GImg* info = a.info + b;
-    if (b == 0 && blockIdx.y == 0 && tid == 0) *a.ticket = 0u;
-    if (M == 0) {
-        if (tid == 0 && blockIdx.y == 1) {
+    if (b == 0 && chunk == 0 && tid == 0) *a.ticket = 0u;
+    const int c0 = chunk * kChunk;
+    const int Mc = min(M - c0, kChunk);
+    if (Mc <= 0) {
+        if (tid == 0 && chunk == 0) {
             GImg z = {0, G_PLAIN, 0, 0, 0, 0u, 0.0f, -1.0f, 0ull, 0ull};
             *info = z;
         }
         return;
     }
-    const float4* boxes = a.boxes + off;
-    const int64_t* classes = a.classes ? a.classes + off : nullptr;
+    const float4* boxes = a.boxes + off + c0;
+    const int64_t* classes = a.classes ? a.classes + off + c0 : nullptr;
+    const float* scores = a.scores + off + c0;
+    const int ccap = (min(a.cap, kChunk) + 7) & ~7;
+    u32* hist = s_dyn;
+    unsigned short* keys = reinterpret_cast<unsigned short*>(s_dyn + NB);
+    unsigned short* oidx = keys + ccap;
+    unsigned short* lut = oidx + ccap;
 
-    if (blockIdx.y == 0) {
-        // ---- stable descending score sort: order[r] = original index, rinv[index] = r ---------------
-        const float* scores = a.scores + off;
-        u32* order = a.order + off;
-        u32* rinv = a.rinv + off;
-        if (SMEM) {
-            const u32* res = s16_sort(M, a.cap, [&](int i) { return desc_key(scores[i]); }, s_dyn);
-            for (int r = tid; r < M; r += NT) {
-                const u32 idx = res[r] >> 16;
-                order[r] = idx;
-                rinv[idx] = (u32)r;
-            }
-        } else {
-            u32 *ka = a.k0 + off, *va = a.v0 + off, *kb = a.k1 + off, *vb = a.v1 + off;
-            for (int i = tid; i < M; i += NT) { ka[i] = desc_key(scores[i]); va[i] = (u32)i; }
-            __syncthreads();
-            radix_sort(ka, va, kb, vb, M, 0, 32, s_dyn, s_dyn + 32 * 256, &s_skip);
-            for (int r = tid; r < M; r += NT) {
-                const u32 idx = va[r];
-                order[r] = idx;
-                rinv[idx] = (u32)r;
-            }
-        }
-        return;
-    }
+    lut[tid] = hilbert_lut_entry(tid >> 8, (u32)(tid >> 4) & 15u, (u32)tid & 15u);
+#pragma unroll
+    for (int k = 0; k < NB / NT; ++k) hist[k * NT + tid] = 0u;
 
-    // ---- reductions (torchvision's boxes.max(), validity, centre range, class range) ------------------
-    const int mode = !classes ? G_PLAIN : ((long long)M * 4 <= a.trick_max_numel ? G_TRICK : G_CLASS);
+    // ---- reductions (torchvision's boxes.max(), validity, centre range, class range, bucket range) ----
+    const int mode = !a.classes ? G_PLAIN : ((long long)M * 4 <= a.trick_max_numel ? G_TRICK : G_CLASS);
     float mx = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
-    int bad = 0, maxcls = 0;
-    for (int i = tid; i < M; i += NT) {
+    int bad = 0, maxcls = 0, bmin = 127, bmax = 0;
+    for (int i = tid; i < Mc; i += NT) {
         const float4 q = boxes[i];
         mx = fmaxf(mx, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
         const bool nan = (q.x != q.x) || (q.y != q.y) || (q.z != q.z) || (q.w != q.w);
@@ -206,6 +267,9 @@ __global__ void __launch_bounds__(NT) graph_sort_kernel(const GArgs a) {
         const float cx = (q.x + q.z) * 0.5f, cy = (q.y + q.w) * 0.5f;
         cmin = fminf(cmin, fminf(cx, cy));
         cmax = fmaxf(cmax, fmaxf(cx, cy));
+        const int bk = (int)area_bucket(q);
+        bmin = min(bmin, bk);
+        bmax = max(bmax, bk);
         if (classes) {
             const long long c = classes[i];
             bad |= (c < 0 || c >= 512) ? 2 : 0;
@@ -214,41 +278,81 @@ __global__ void __launch_bounds__(NT) graph_sort_kernel(const GArgs a) {
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
     maxcls = __reduce_max_sync(0xffffffffu, maxcls);
-    if (lane == 0) { s_flag[warp] = bad; s_maxcls[warp] = maxcls; }
+    bmin = __reduce_min_sync(0xffffffffu, bmin);
+    bmax = __reduce_max_sync(0xffffffffu, bmax);
+    if (lane == 0) { s_flag[warp] = bad; s_maxcls[warp] = maxcls; s_bmin[warp] = bmin; s_bmax[warp] = bmax; }
     mx = block_reduce_minmax<NT>(mx, true, s_f, lane, warp);
     cmin = block_reduce_minmax<NT>(cmin, false, s_f, lane, warp);
     cmax = block_reduce_minmax<NT>(cmax, true, s_f, lane, warp);
-    bad = 0; maxcls = 0;
-    for (int w = 0; w < NT / 32; ++w) { bad |= s_flag[w]; maxcls = max(maxcls, s_maxcls[w]); }
-    float s_off = mx + 1.0f;                            // boxes.py:99
+    bad = 0; maxcls = 0; bmin = 127; bmax = 0;
+    for (int w = 0; w < NT / 32; ++w) {
+        bad |= s_flag[w]; maxcls = max(maxcls, s_maxcls[w]); bmin = min(bmin, s_bmin[w]); bmax = max(bmax, s_bmax[w]);
+    }
+    // torchvision's offset step (boxes.py:99); only single-chunk images can be in trick mode (4*M <= 100000)
+    float s_off = mx + 1.0f;
     if (bad & 4) s_off = __int_as_float(0x7fc00000);    // torch max propagates NaN
     if (mode == G_TRICK && !((float)maxcls * s_off + fabsf(mx) <= 1e17f)) bad |= 1;
     const bool exact = (bad & 1) || !a.thr_fast_ok;
+    // 2: class ids beyond the key; 4: boxes or threshold the half-precision filter cannot serve (NaN/Inf, inverted,
+    // |coordinate| > 1e17, thr outside [0.03, 1e30]).  Both are decided by the resolve kernel's greedy pass.
+    const int flags = ((bad & 2) ? 2 : 0) | (exact ? 4 : 0);
+    if (flags && tid == 0) atomicOr(a.iflags + b, flags);
 
-    // ---- spatial order, stable by original index -----------------------------------------------------
-    const float qs = (cmax > cmin) ? 255.0f / (cmax - cmin) : 0.0f;
-    u32* pos = a.pos + off;
-    if (SMEM) {
-        const u32* res = s16_sort(M, a.cap, [&](int i) { return spatial_key(boxes[i], classes, i, cmin, qs); }, s_dyn);
-        for (int p = tid; p < M; p += NT) pos[p] = res[p] >> 16;
-    } else {
-        u32 *ka = a.k2 + off, *va = a.v2 + off, *kb = a.srank + off, *vb = a.scls + off;  // scratch until the gather
-        for (int i = tid; i < M; i += NT) {
-            ka[i] = spatial_key(boxes[i], classes, i, cmin, qs);
-            va[i] = (u32)i;
-        }
-        __syncthreads();
-        radix_sort(ka, va, kb, vb, M, 0, 32, s_dyn, s_dyn + 32 * 256, &s_skip);
-        for (int p = tid; p < M; p += NT) pos[p] = va[p];
+    // ---- key layout of this chunk ----
+    KeyBits kb;
+    {
+        const int nb_cls = classes ? 32 - __clz(maxcls) : 0;                 // <= 9
+        const int span_bits = 32 - __clz(max(bmax - bmin, 0));             // <= 7
+        const int nb_bkt = min(span_bits, kKeyBits - nb_cls);
+        const int nb_curve = kKeyBits - nb_cls - nb_bkt;
+        kb.bkt_drop = span_bits - nb_bkt;
+        kb.cls_shift = nb_bkt + nb_curve;
+        kb.bkt_shift = nb_curve;
+        kb.curve_drop = 16 - nb_curve;
+        kb.bmin = (u32)bmin;
+        kb.cmin = cmin;
+        kb.qs = (cmax > cmin) ? 255.0f / (cmax - cmin) : 0.0f;
     }
-    if (tid == 0) {
+    // (the block reductions above ended with a barrier: lut and the zeroed histogram are visible)
+
+    // ---- counting sort by key: histogram, exclusive scan, scatter ----
+    for (int i = tid; i < Mc; i += NT) {
+        const u32 k = spatial_key(boxes[i], classes, i, kb, lut);
+        keys[i] = (unsigned short)k;
+        atomicAdd(&hist[k], 1u);
+    }
+    __syncthreads();
+    {
+        constexpr int PER = NB / NT;   // 16 consecutive bins per thread
+        u32 v[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { v[k] = hist[tid * PER + k]; sum += v[k]; }
+        u32 inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        u32 base = inc - sum;
+        for (int w = 0; w < warp; ++w) base += s_scan[w];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { hist[tid * PER + k] = base; base += v[k]; }
+    }
+    __syncthreads();
+    for (int i = tid; i < Mc; i += NT) oidx[atomicAdd(&hist[keys[i]], 1u)] = (unsigned short)i;
+    __syncthreads();
+
+    // ---- position -> original index (the gather runs as its own, machine-wide launch) ----
+    u32* pos = a.pos + off + c0;
+    for (int p = tid; p < Mc; p += NT) pos[p] = (u32)c0 + oidx[p];
+    if (tid == 0 && chunk == 0) {
         GImg o;
-        o.M = M; o.mode = mode; o.exact = exact ? 1 : 0;
-        // 2: class ids beyond the sort key; 4: boxes or threshold the half-precision filter cannot serve (NaN/Inf,
-        // inverted, |coordinate| > 1e17, thr outside [0.03, 1e30]).  Both are decided by the resolve kernel's greedy pass.
-        o.overflow = ((bad & 2) ? 2 : 0) | (exact ? 4 : 0);
+        o.M = M; o.mode = mode; o.exact = 0;
+        o.overflow = 0;   // the edge and resolve kernels look at iflags[b]
         o.n_tiles = (M + kTile - 1) / kTile; o.n_edges = 0u; o.s_off = s_off;
-        o.t2 = exact ? -1.0f : a.thr * (1.0f - 9.765625e-4f);
+        o.t2 = a.thr * (1.0f - 9.765625e-4f);
         o.n_evals = 0ull;
         o.n_cands = 0ull;
         *info = o;
@@ -256,8 +360,18 @@ __global__ void __launch_bounds__(NT) graph_sort_kernel(const GArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// gather in position order (coordinate-offset trick, boxes.py:99-101) + tile / sub-tile statistics
+// gather in position order (coordinate-offset trick, boxes.py:99-101) + tile / sub-tile statistics: a warp per
+// 32-box tile, the whole machine.  Minima / maxima go through the integer warp-reduce unit (REDUX) on
+// order-preserving integer images of the floats: 12 reductions per tile instead of 80 shuffle + min/max steps.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 f2ord(const float f) {
+    const u32 u = __float_as_uint(f);
+    return u ^ ((u32)((int)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(const u32 o) {
+    return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
 __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArgs a) {
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const GImg info = a.info[b];
@@ -268,14 +382,14 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
     const float4* boxes = a.boxes + off;
     const int64_t* classes = a.classes ? a.classes + off : nullptr;
     const int p = t * kTile + lane;
-    float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY, amin = INFINITY, amax = -INFINITY;
-    u32 c0 = 0xffffffffu, c1 = 0u;
+    u32 x1 = 0xffffffffu, y1 = 0xffffffffu, x2 = 0u, y2 = 0u, amin = 0xffffffffu, amax = 0u, c0 = 0xffffffffu, c1 = 0u;
     float4* sbo = a.sboxes + (size_t)b * a.scap;
     if (p >= M && p < ((M + kSub - 1) & ~(kSub - 1)))   // the edge kernel stages whole sub-tiles: far-away padding boxes
         sbo[p] = make_float4(1e18f, 1e18f, 2e18f, 2e18f);
     if (p < M) {
         const u32 idx = a.pos[off + p];
         float4 q = boxes[idx];
+        const float sc = a.scores[off + idx];
         u32 c = 0;
         if (classes) c = (u32)classes[idx];
         if (info.mode == G_TRICK) {
@@ -284,32 +398,32 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
         }
         const u32 cls = (info.mode == G_CLASS) ? c : 0u;
         sbo[p] = q;
-        a.srank[off + p] = a.rinv[off + idx];
+        a.skey[off + p] = desc_key(sc);
+        a.sidx[off + p] = idx;
         a.scls[off + p] = cls;
-        x1 = q.x; y1 = q.y; x2 = q.z; y2 = q.w;
-        amin = amax = (q.z - q.x) * (q.w - q.y);
+        x1 = f2ord(q.x); y1 = f2ord(q.y); x2 = f2ord(q.z); y2 = f2ord(q.w);
+        amin = amax = f2ord((q.z - q.x) * (q.w - q.y));
         c0 = c1 = cls;
     }
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-        y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-        x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o));
-        y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
-        amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
-        c1 = max(c1, __shfl_xor_sync(0xffffffffu, c1, o));
-        if (o == kSub / 2 && (lane & (kSub - 1)) == 0) {  // statistics of this lane's kSub-box sub-tile
-            float4* ss = a.sstat + (((size_t)b * a.tcap + t) * kSubs + (lane / kSub)) * 2;
-            ss[0] = make_float4(x1, y1, x2, y2);
-            ss[1] = make_float4(amin, amax, 0.0f, 0.0f);
-        }
+    const unsigned sm = 0xffu << (lane & 24);   // this lane's 8-box sub-tile
+    const u32 sx1 = __reduce_min_sync(sm, x1), sy1 = __reduce_min_sync(sm, y1);
+    const u32 sx2 = __reduce_max_sync(sm, x2), sy2 = __reduce_max_sync(sm, y2);
+    const u32 samin = __reduce_min_sync(sm, amin), samax = __reduce_max_sync(sm, amax);
+    if ((lane & (kSub - 1)) == 0) {
+        float4* ss = a.sstat + (((size_t)b * a.tcap + t) * kSubs + (lane / kSub)) * 2;
+        // an empty sub-tile (beyond M) keeps +inf/-inf style bounds: it never passes a test (and is never visited)
+        ss[0] = make_float4(ord2f(sx1), ord2f(sy1), ord2f(sx2), ord2f(sy2));
+        ss[1] = make_float4(ord2f(samin), ord2f(samax), 0.0f, 0.0f);
     }
+    const u32 tx1 = __reduce_min_sync(0xffffffffu, sx1), ty1 = __reduce_min_sync(0xffffffffu, sy1);
+    const u32 tx2 = __reduce_max_sync(0xffffffffu, sx2), ty2 = __reduce_max_sync(0xffffffffu, sy2);
+    const u32 tamin = __reduce_min_sync(0xffffffffu, samin), tamax = __reduce_max_sync(0xffffffffu, samax);
+    c0 = __reduce_min_sync(0xffffffffu, c0);
+    c1 = __reduce_max_sync(0xffffffffu, c1);
     if (lane == 0) {
         float4* ts = a.tstat + ((size_t)b * a.tcap + t) * 2;
-        ts[0] = make_float4(x1, y1, x2, y2);
-        ts[1] = make_float4(amin, amax, __uint_as_float(c0), __uint_as_float(c1));
+        ts[0] = make_float4(ord2f(tx1), ord2f(ty1), ord2f(tx2), ord2f(ty2));
+        ts[1] = make_float4(ord2f(tamin), ord2f(tamax), __uint_as_float(c0), __uint_as_float(c1));
     }
 }
 
@@ -407,9 +521,9 @@ __device__ __forceinline__ void edge_flush(const GArgs& a, EdgeWarp& w, int b, u
 // Exact stage: the queued (row, column) pairs, one per lane.  torchvision's predicate with the division-free
 // margin test; ambiguous lanes redo the exact fma/div arithmetic with the higher-scored box as `a`.
 __device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I,
-                                          const float4* __restrict__ sb, const u32* __restrict__ srank,
-                                          const u32* __restrict__ scls, uint2* __restrict__ edges, int& n_cand,
-                                          int& n_buf) {
+                                          const float4* __restrict__ sb, const u32* __restrict__ skey,
+                                          const u32* __restrict__ sidx, const u32* __restrict__ scls,
+                                          uint2* __restrict__ edges, int& n_cand, int& n_buf) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float kEps = 9.5367431640625e-07f;     // 2^-20
@@ -429,7 +543,9 @@ __device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const 
             if (qp > rp && qp < M && rp < M) {   // each unordered pair once; padding columns of the last sub-tile never
                 const float4 r = sb[rp];
                 const float4 q = sb[qp];
-                const u32 rrank = srank[rp], crank = srank[qp];
+                // score order without the score sort: descending-score key, ties by the lower original index
+                const u32 rk = skey[rp], ck = skey[qp], ri = sidx[rp], ci = sidx[qp];
+                const bool row_first = rk < ck || (rk == ck && ri < ci);
                 const float qw = q.z - q.x, qh = q.w - q.y, rw = r.z - r.x, rh = r.w - r.y;
                 const float qarea = qw * qh, rarea = rw * rh;
                 const float left = fmaxf(r.x, q.x), right = fminf(r.z, q.z);
@@ -442,15 +558,15 @@ __device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const 
                 const float d = inter - tt;
                 bool pr = d > 0.0f;
                 if (!(fabsf(d) > __fmaf_rn(tt, kEps, kTiny))) {
-                    const bool row_a = rrank < crank;   // torchvision devIoU with a = the higher-scored box
+                    const bool row_a = row_first;   // torchvision devIoU with a = the higher-scored box
                     const float sa = row_a ? rarea : qarea;
                     const float bw = row_a ? qw : rw, bh = row_a ? qh : rh;
                     const float den = __fmaf_rn(bw, bh, sa) - inter;
                     pr = (inter / den) > thr;
                 }
                 fin = pr && (!class_mode || scls[qp] == scls[rp]);
-                rlo = min(rrank, crank);
-                rhi = max(rrank, crank);
+                rlo = row_first ? ri : ci;   // edge = (higher-scored, lower-scored) ORIGINAL indices; the resolve
+                rhi = row_first ? ci : ri;   // kernel turns them into score ranks
             }
         }
         const unsigned em = __ballot_sync(0xffffffffu, fin);
@@ -469,8 +585,9 @@ __device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const 
 // statistics (one half2 step per dimension pair), the surviving (row, slot) items are packed, and every
 // iteration of the pair loop filters 8 items x 8 columns: 64 pairs on 32 lanes whatever the culling pattern.
 __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I, int head,
-                                           const float4* __restrict__ sb, const u32* __restrict__ srank,
-                                           const u32* __restrict__ scls, uint2* __restrict__ edges, const Frame& f,
+                                           const float4* __restrict__ sb, const u32* __restrict__ skey,
+                                           const u32* __restrict__ sidx, const u32* __restrict__ scls,
+                                           uint2* __restrict__ edges, const Frame& f,
                                            const int n_slots, const bool rvalid, const u32 r_lo, const u32 r_hi,
                                            const u32 r_wh_t, const u32 r_ar, u32& n_evals, u32& n_cands,
                                            int& n_cand, int& n_buf) {
@@ -554,7 +671,7 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
         n_cand += __popc(m1);
         if (n_cand >= kTile) {
             n_cands += (u32)n_cand;
-            cand_process(a, w, info, b, I, sb, srank, scls, edges, n_cand, n_buf);
+            cand_process(a, w, info, b, I, sb, skey, sidx, scls, edges, n_cand, n_buf);
         }
     }
     __syncwarp();
@@ -574,11 +691,12 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         if (ticket >= total) break;
         const int I = (int)(ticket / (u32)a.B), b = (int)(ticket % (u32)a.B);  // all images' tile 0 first
         const GImg info = a.info[b];
-        if (I >= info.n_tiles || info.overflow) continue;
+        if (I >= info.n_tiles || a.iflags[b]) continue;
         const int M = info.M;
         const size_t off = (size_t)b * a.cap;
         const float4* sb = a.sboxes + (size_t)b * a.scap;
-        const u32* srank = a.srank + off;
+        const u32* skey = a.skey + off;
+        const u32* sidx = a.sidx + off;
         const u32* scls = a.scls + off;
         const float4* ts = a.tstat + (size_t)b * a.tcap * 2;
         const float4* ss = a.sstat + (size_t)b * a.tcap * kSubs * 2;
@@ -586,6 +704,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         const float t2 = info.t2;
         const float t3 = a.t3;
         const bool class_mode = info.mode == G_CLASS;
+        const bool class_sorted = class_mode && a.n_chunks == 1;   // one chunk: tiles are ordered by class
 
         // ---- the tile's local frame ----
         const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
@@ -657,10 +776,10 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                 float4 jb = make_float4(0.f, 0.f, 0.f, 0.f), ja = jb;
                 if (ok) { jb = ts[Jl * 2]; ja = ts[Jl * 2 + 1]; }
                 if (class_mode) {
-                    // tiles are ordered by class: nothing beyond the last tile that can hold icmax
                     const bool beyond = ok && __float_as_uint(ja.z) > icmax;
                     ok = ok && !beyond && __float_as_uint(ja.w) >= icmin;
-                    if (__ballot_sync(0xffffffffu, beyond) == 0xffffffffu) {
+                    // tiles ordered by class (single chunk): nothing beyond the last tile that can hold icmax
+                    if (class_sorted && __ballot_sync(0xffffffffu, beyond) == 0xffffffffu) {
                         J0 = info.n_tiles - 32;  // next round is the tail
                         continue;
                     }
@@ -709,7 +828,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                 // level 3: chunks of 8 sub-tiles
                 int head = 0;
                 for (; n_q - head >= kSlots; head += kSlots)
-                    edge_chunk(a, w, info, b, I, head, sb, srank, scls, edges, f, n_tail, rvalid, r_lo, r_hi, r_wh_t, r_ar,
+                    edge_chunk(a, w, info, b, I, head, sb, skey, sidx, scls, edges, f, n_tail, rvalid, r_lo, r_hi, r_wh_t, r_ar,
                                n_evals, n_cands, n_cand, n_buf);
                 if (head) {  // move the < 8 leftovers to the front
                     const int rem = n_q - head;
@@ -726,7 +845,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         }
         if (n_cand) {
             n_cands += (u32)n_cand;
-            cand_process(a, w, info, b, I, sb, srank, scls, edges, n_cand, n_buf);
+            cand_process(a, w, info, b, I, sb, skey, sidx, scls, edges, n_cand, n_buf);
         }
         edge_flush(a, w, b, edges, n_buf);
         if (lane == 0 && n_evals) {
@@ -896,7 +1015,7 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
         if (tid == 0) a.n_keep[b] = 0;
         return;
     }
-    if (info.overflow || (u64)info.n_edges > a.edges_per_img) {
+    if (a.iflags[b] || (u64)info.n_edges > a.edges_per_img) {
         greedy_resolve(a, info, b, *reinterpret_cast<GreedySmem*>(s_bits));
         return;
     }
@@ -908,8 +1027,15 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
         U[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
         K[w] = 0u; fK[w] = 0u; fU[w] = 0u;
     }
-    const uint2* edges = a.edges + (u64)b * a.edges_per_img;
+    uint2* edges = a.edges + (u64)b * a.edges_per_img;
     const u32 E = info.n_edges;
+    {   // the edge kernel recorded ORIGINAL indices (it does not wait for the score sort): to score ranks, once
+        const u32* __restrict__ rinv = a.rinv + (size_t)b * a.cap;
+        for (u32 e = tid; e < E; e += kResolveThreads) {
+            const uint2 sd = edges[e];
+            edges[e] = make_uint2(rinv[sd.x], rinv[sd.y]);
+        }
+    }
     __syncthreads();
     for (;;) {
         for (u32 e = tid; e < E; e += kResolveThreads) {
@@ -970,7 +1096,7 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
 
 // ---- host side -------------------------------------------------------------------------------
 struct GLayout {
-    size_t k[6], order, rinv, pos, sboxes, srank, scls, tstat, sstat, info, ticket, edges, total;
+    size_t k[4], order, rinv, pos, sboxes, skey, sidx, scls, tstat, sstat, info, iflags, ticket, edges, total;
 };
 
 static inline size_t g_align(size_t x) { return (x + 255) / 256 * 256; }
@@ -980,16 +1106,19 @@ static GLayout graph_layout(int B, int cap) {
     size_t o = 0;
     const size_t n = (size_t)B * cap;
     const size_t tcap = ((size_t)cap + kTile - 1) / kTile;
-    for (int i = 0; i < 6; ++i) { L.k[i] = o; o = g_align(o + n * 4); }
+    const size_t nk = cap > kS16MaxM ? n : 0;   // ping-pong buffers: only the ballot score sort of large images
+    for (int i = 0; i < 4; ++i) { L.k[i] = o; o = g_align(o + nk * 4); }
     L.order = o; o = g_align(o + n * 4);
     L.rinv = o; o = g_align(o + n * 4);
     L.pos = o; o = g_align(o + n * 4);
     L.sboxes = o; o = g_align(o + (size_t)B * (((size_t)cap + kSub - 1) / kSub * kSub) * 16);
-    L.srank = o; o = g_align(o + n * 4);
+    L.skey = o; o = g_align(o + n * 4);
+    L.sidx = o; o = g_align(o + n * 4);
     L.scls = o; o = g_align(o + n * 4);
     L.tstat = o; o = g_align(o + (size_t)B * tcap * 32);
     L.sstat = o; o = g_align(o + (size_t)B * tcap * kSubs * 32);
     L.info = o; o = g_align(o + (size_t)B * sizeof(GImg));
+    L.iflags = o; o = g_align(o + (size_t)B * sizeof(int));
     L.ticket = o; o = g_align(o + 256);
     L.edges = o;
     L.total = o;
@@ -997,6 +1126,36 @@ static GLayout graph_layout(int B, int cap) {
 }
 
 size_t graph_min_workspace(int B, int cap) { return graph_layout(B, cap).total + (size_t)B * 8; }
+
+// The score sort only feeds the resolve kernel, so it runs on a side stream between two events (fork after the
+// caller's previous work, join before the resolve kernel) and overlaps with the spatial kernel and the edge
+// discovery; under stream capture the fork/join becomes two parallel branches of the graph.  One side stream and a
+// ring of event pairs per device, created on first use (never during a capture: a warm-up call comes first).
+struct ForkJoin {
+    cudaStream_t side = nullptr;
+    static constexpr int kRing = 32;
+    cudaEvent_t fork[kRing] = {}, join[kRing] = {};
+    std::atomic<unsigned> next{0};
+    bool ok = false;
+};
+static ForkJoin* fork_join_for_device() {
+    static std::mutex mu;
+    static ForkJoin* per_dev[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!per_dev[dev]) {
+        ForkJoin* f = new ForkJoin();
+        bool ok = cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; ok && i < ForkJoin::kRing; ++i)
+            ok = cudaEventCreateWithFlags(&f->fork[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&f->join[i], cudaEventDisableTiming) == cudaSuccess;
+        f->ok = ok;
+        if (!ok) cudaGetLastError();
+        per_dev[dev] = f;
+    }
+    return per_dev[dev]->ok ? per_dev[dev] : nullptr;
+}
 
 int graph_nms(const float* boxes, const float* scores, const int64_t* classes, const int* counts, int B, int cap,
               double iou_threshold, long long trick_max_numel, int64_t* keep, int* n_keep, void* ws,
@@ -1008,6 +1167,7 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     GArgs a;
     a.boxes = reinterpret_cast<const float4*>(boxes); a.scores = scores; a.classes = classes; a.counts = counts;
     a.B = B; a.cap = cap; a.tcap = (cap + kTile - 1) / kTile; a.scap = (cap + kSub - 1) / kSub * kSub;
+    a.n_chunks = (cap + kChunk - 1) / kChunk;
     a.thr = (float)iou_threshold;
     a.thr_fast_ok = (a.thr >= 0.03f && a.thr <= 1e30f) ? 1 : 0;
     a.t3 = a.thr * (1.0f - 0.015625f);
@@ -1020,33 +1180,53 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
         a.hexp = a.thr >= 0.35f ? 5 : (a.thr >= 0.1f ? 4 : 3);   // keeps K * (row area) inside the half range
     }
     a.trick_max_numel = trick_max_numel;
-    a.k0 = (u32*)(w + L.k[0]); a.v0 = (u32*)(w + L.k[1]); a.k1 = (u32*)(w + L.k[2]);
-    a.v1 = (u32*)(w + L.k[3]); a.k2 = (u32*)(w + L.k[4]); a.v2 = (u32*)(w + L.k[5]);
+    a.k0 = (u32*)(w + L.k[0]); a.v0 = (u32*)(w + L.k[1]); a.k1 = (u32*)(w + L.k[2]); a.v1 = (u32*)(w + L.k[3]);
     a.order = (u32*)(w + L.order); a.rinv = (u32*)(w + L.rinv); a.pos = (u32*)(w + L.pos);
-    a.sboxes = (float4*)(w + L.sboxes); a.srank = (u32*)(w + L.srank); a.scls = (u32*)(w + L.scls);
+    a.sboxes = (float4*)(w + L.sboxes); a.skey = (u32*)(w + L.skey); a.sidx = (u32*)(w + L.sidx); a.scls = (u32*)(w + L.scls);
     a.tstat = (float4*)(w + L.tstat);
     a.sstat = (float4*)(w + L.sstat);
     a.info = (GImg*)(w + L.info);
+    a.iflags = (int*)(w + L.iflags);
     a.ticket = (u32*)(w + L.ticket);
     a.edges = (uint2*)(w + L.edges);
     a.edges_per_img = (ws_bytes - L.edges) / 8 / (size_t)B;
     a.keep = keep; a.n_keep = n_keep;
 
+    // ---- fork: score order on the side stream ----
+    ForkJoin* fj = fork_join_for_device();
+    cudaStream_t ss = st;
+    int slot = 0;
+    if (fj) {
+        slot = (int)(fj->next.fetch_add(1u) % ForkJoin::kRing);
+        YB_CUDA(cudaEventRecord(fj->fork[slot], st));
+        YB_CUDA(cudaStreamWaitEvent(fj->side, fj->fork[slot], 0));
+        ss = fj->side;
+    }
     if (cap <= kS16MaxM) {
         const size_t sort_smem = s16_smem_bytes(cap);
-        YB_CUDA(cudaFuncSetAttribute(graph_sort_kernel<kS16Threads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        YB_CUDA(cudaFuncSetAttribute(graph_score_kernel<kS16Threads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sort_smem));
-        YB_LAUNCH("graph_sort_kernel", st,
-                  (graph_sort_kernel<kS16Threads, true><<<dim3(B, 2), kS16Threads, sort_smem, st>>>(a)));
+        YB_LAUNCH("graph_score_kernel", ss, (graph_score_kernel<kS16Threads, true><<<B, kS16Threads, sort_smem, ss>>>(a)));
     } else {
         const size_t sort_smem = (32 * 256 + 256) * sizeof(u32);
-        YB_LAUNCH("graph_sort_kernel", st,
-                  (graph_sort_kernel<kSortThreads, false><<<dim3(B, 2), kSortThreads, sort_smem, st>>>(a)));
+        YB_LAUNCH("graph_score_kernel", ss, (graph_score_kernel<kSortThreads, false><<<B, kSortThreads, sort_smem, ss>>>(a)));
+    }
+    if (fj) YB_CUDA(cudaEventRecord(fj->join[slot], fj->side));
+
+    // ---- main branch: spatial order + gather, edge discovery ----
+    YB_CUDA(cudaMemsetAsync(a.iflags, 0, (size_t)B * sizeof(int), st));
+    {
+        const size_t smem = spatial_smem_bytes(cap < kChunk ? cap : kChunk);
+        YB_CUDA(cudaFuncSetAttribute(graph_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        YB_LAUNCH("graph_spatial_kernel", st, graph_spatial_kernel<<<dim3(a.n_chunks, B), kSpThreads, smem, st>>>(a));
     }
     const dim3 ggrid((a.tcap + kGatherThreads / 32 - 1) / (kGatherThreads / 32), B);
     YB_LAUNCH("graph_gather_kernel", st, graph_gather_kernel<<<ggrid, kGatherThreads, 0, st>>>(a));
     const int ctas = sm_count() * 4;  // 4 resident CTAs per SM (launch bounds)
     YB_LAUNCH("graph_edge_kernel", st, graph_edge_kernel<<<ctas, kEdgeThreads, 0, st>>>(a));
+
+    // ---- join, resolve ----
+    if (fj) YB_CUDA(cudaStreamWaitEvent(st, fj->join[slot], 0));
     static_assert(kResolveThreads == 2 * kGreedyT, "greedy_resolve splits the CTA in two halves");
     size_t dyn = (size_t)((cap + 31) / 32) * 4 * 4;
     if (dyn < sizeof(GreedySmem)) dyn = sizeof(GreedySmem);
