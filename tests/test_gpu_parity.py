@@ -944,6 +944,63 @@ def test_full_size_properties(yb, nc, B, conf, algo):
         assert np.array_equal(keep.cpu().numpy(), want)
 
 
+def _check_image_against_oracle_and_torchvision(yb, det, heads_cpu, b, img, nc, conf, iou):
+    """One image of a detect_batch result: candidates vs the oracle's filter, keep set bit-exact vs
+    torchvision.ops.batched_nms on CUDA tensors (the reference's GPU path, train.py:1232-1233) and the C oracle."""
+    import torchvision
+    m, k = int(det["counts"][b]), int(det["n_keep"][b])
+    bx, sc, cl = det["boxes"][b, :m], det["scores"][b, :m], det["classes"][b, :m]
+    rb, rs, rc = R.candidates([h[b:b + 1] for h in heads_cpu], ANCH, img, nc, conf)
+    assert m == rb.shape[0] and torch.equal(cl.cpu(), rc)
+    close(bx, rb, atol=1e-5 * img)
+    close(sc, rs, atol=1e-8)
+    want_tv = torchvision.ops.batched_nms(bx, sc, cl, iou)          # picks the per-class loop above 25,000 boxes
+    got = det["keep"][b, :k]
+    assert torch.equal(got, want_tv), (k, int(want_tv.numel()))
+    want = R.batched_nms_indices(bx.cpu().numpy(), sc.cpu().numpy(), cl.cpu().numpy(), iou, "cuda", "cuda")
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_config3_full_size_1280_nc80_dense(yb):
+    """BASELINE configs[3] at its real per-image size: nc=80 heads at 1280x1280, conf 0.001 -> 100,800 candidates per
+    image (4 spatial chunks, the ballot score sort, torchvision's per-class regime).  B=2 keeps the oracle fast."""
+    nc, img, B, conf, iou = 80, 1280, 2, 0.001, 0.4
+    g = torch.Generator().manual_seed(1234)
+    heads = [torch.randn(B, G, G, 3, 5 + nc, generator=g) for G in (160, 80, 40)]
+    det = yb.detect_batch([h.cuda() for h in heads], ANCH, img, nc, conf, iou)
+    assert det["counts"].cpu().tolist() == [100800, 100800]
+    for b in range(B):
+        _check_image_against_oracle_and_torchvision(yb, det, heads, b, img, nc, conf, iou)
+    # the dense bitmask algorithm agrees
+    d1 = yb.detect_batch([h[:1].cuda() for h in heads], ANCH, img, nc, conf, iou, algo=yb.NMS_BITMASK)
+    k = int(det["n_keep"][0])
+    assert int(d1["n_keep"][0]) == k and torch.equal(d1["keep"][0, :k], det["keep"][0, :k])
+
+
+def test_config2_full_batch_640_nc80_dense(yb):
+    """BASELINE configs[2] at its real batch: nc=80, 640x640, B=64, conf 0.001 (25,200 candidates per image: just above
+    torchvision's 25,000-box switch to the per-class loop); first, middle and last image against the oracle."""
+    nc, img, B, conf, iou = 80, 640, 64, 0.001, 0.4
+    g = torch.Generator().manual_seed(1234)
+    heads = [torch.randn(B, G, G, 3, 5 + nc, generator=g) for G in (80, 40, 20)]
+    det = yb.detect_batch([h.cuda() for h in heads], ANCH, img, nc, conf, iou)
+    assert bool((det["counts"] == 25200).all()) and bool((det["n_keep"] > 0).all())
+    for b in (0, 31, 63):
+        _check_image_against_oracle_and_torchvision(yb, det, heads, b, img, nc, conf, iou)
+
+
+def test_config1_conf_sweep_keep_sets(yb):
+    """configs[1] heads (nc=1, 640x640) at the three thresholds of SURVEY 8d: 0.5 (coordinate-trick regime, 12.6 K
+    candidates), 0.25 and 0.001 (25,200 > 25,000: per-class regime) for two images each."""
+    nc, img, B, iou = 1, 640, 4, 0.4
+    g = torch.Generator().manual_seed(1234)
+    heads = [torch.randn(B, G, G, 3, 5 + nc, generator=g) for G in (80, 40, 20)]
+    for conf in (0.5, 0.25, 0.001):
+        det = yb.detect_batch([h.cuda() for h in heads], ANCH, img, nc, conf, iou)
+        for b in (0, 3):
+            _check_image_against_oracle_and_torchvision(yb, det, heads, b, img, nc, conf, iou)
+
+
 def test_launch_counter_and_library(yb):
     lib = yb._lib.lib()
     before = lib.yb_launch_count()

@@ -80,6 +80,85 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
     }
 }
 
+// Short rows (5..8 floats: nc <= 3, e.g. the reference's single-class 'cone' model): two thirds of the elements
+// need a sigmoid, so the flat walk's per-element (row, channel) bookkeeping costs as much as the arithmetic.  Here a
+// thread owns R = 4/gcd(ROW,4) whole rows = ROW*R/4 float4 vectors (still fully coalesced: consecutive threads own
+// consecutive segments), decomposes the row index once per row and runs straight-line code.
+template <int ROW, bool BWD>
+__global__ void __launch_bounds__(256) decode_rows_kernel(const DecodeArgs a) {
+    constexpr int R = (ROW % 4 == 0) ? 1 : ((ROW % 2 == 0) ? 2 : 4);
+    constexpr int NV = ROW * R / 4;
+    const uint32_t n_groups = a.n_elem / (uint32_t)(ROW * R);   // whole groups; the remainder rows go to the tail below
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const float4* __restrict__ in4 = reinterpret_cast<const float4*>(a.pred);
+    const float4* __restrict__ g4 = reinterpret_cast<const float4*>(a.grad_out);
+    float4* __restrict__ out4 = reinterpret_cast<float4*>(a.out);
+    for (uint32_t gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < n_groups; gidx += stride) {
+        float x[NV * 4], g[NV * 4], o[NV * 4];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 t = __ldcs(in4 + (size_t)gidx * NV + v);
+            x[4 * v] = t.x; x[4 * v + 1] = t.y; x[4 * v + 2] = t.z; x[4 * v + 3] = t.w;
+            if (BWD) {
+                const float4 u = __ldcs(g4 + (size_t)gidx * NV + v);
+                g[4 * v] = u.x; g[4 * v + 1] = u.y; g[4 * v + 2] = u.z; g[4 * v + 3] = u.w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const uint32_t r = gidx * R + k;
+            uint32_t cell, an, gy_b, gx, gy, bi;
+            a.d_A.divmod(r, cell, an);
+            a.d_W.divmod(cell, gy_b, gx);
+            a.d_H.divmod(gy_b, bi, gy);
+            const float aw = __ldg(a.anchors + an * 2), ah = __ldg(a.anchors + an * 2 + 1);
+            const float* xr = x + k * ROW;
+            float* orow = o + k * ROW;
+            if (!BWD) {
+                orow[0] = decode_xy(xr[0], (float)gx, a.k.inv_w);
+                orow[1] = decode_xy(xr[1], (float)gy, a.k.inv_h);
+                orow[2] = decode_wh(xr[2], aw, a.k.inv_img);
+                orow[3] = decode_wh(xr[3], ah, a.k.inv_img);
+#pragma unroll
+                for (int c = 4; c < ROW; ++c) orow[c] = xr[c];
+            } else {
+                const float* gr = g + k * ROW;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {   // autograd order of train.py:758-759,773-774, as in decode_elem
+                    const float s = sigmoidf_ref(xr[c]);
+                    const float ds = (1.0f - s) * s;
+                    if (c < 2) {
+                        orow[c] = ((gr[c] * (c == 0 ? a.k.inv_w : a.k.inv_h)) * 2.0f) * ds;
+                    } else {
+                        const float u = 2.0f * s;
+                        const float gp = gr[c] * ((c == 2 ? aw : ah) * a.k.inv_img);
+                        orow[c] = ((gp * (2.0f * u)) * 2.0f) * ds;
+                    }
+                }
+#pragma unroll
+                for (int c = 4; c < ROW; ++c) orow[c] = gr[c];
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            __stcs(out4 + (size_t)gidx * NV + v, make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]));
+    }
+    // the last (< R) rows
+    const uint32_t e0 = n_groups * (uint32_t)(ROW * R);
+    if (blockIdx.x == 0 && e0 + threadIdx.x < a.n_elem) {
+        const uint32_t e = e0 + threadIdx.x;
+        uint32_t r, c;
+        a.d_row.divmod(e, r, c);
+        a.out[e] = decode_elem<BWD>(a, r, c, a.pred[e], BWD ? a.grad_out[e] : 0.f);
+    }
+}
+
+template <int ROW>
+static void decode_rows_launch(bool bwd, const DecodeArgs& a, int blocks, cudaStream_t st) {
+    if (bwd) decode_rows_kernel<ROW, true><<<blocks, 256, 0, st>>>(a);
+    else     decode_rows_kernel<ROW, false><<<blocks, 256, 0, st>>>(a);
+}
+
 static int decode_launch(bool bwd, const float* pred, const float* anchors, const float* grad_out,
                          float* out, int B, int H, int W, int A, int nc, float img_size,
                          void* stream) {
@@ -103,6 +182,20 @@ static int decode_launch(bool bwd, const float* pred, const float* anchors, cons
     unsigned long long cap = (unsigned long long)sm_count() * 8 * 4;
     int blocks = (int)(want < 1 ? 1 : (want < cap ? want : cap));
     cudaStream_t st = (cudaStream_t)stream;
+    if (a.row <= 8) {   // short rows: whole rows per thread
+        const int R = (a.row % 4 == 0) ? 1 : ((a.row % 2 == 0) ? 2 : 4);
+        unsigned long long groups = n / (a.row * R);
+        unsigned long long w2 = (groups + threads - 1) / threads;
+        blocks = (int)(w2 < 1 ? 1 : (w2 < cap ? w2 : cap));
+        const char* name = bwd ? "decode_bwd_kernel" : "decode_fwd_kernel";
+        switch (a.row) {
+            case 5: YB_LAUNCH(name, st, decode_rows_launch<5>(bwd, a, blocks, st)); break;
+            case 6: YB_LAUNCH(name, st, decode_rows_launch<6>(bwd, a, blocks, st)); break;
+            case 7: YB_LAUNCH(name, st, decode_rows_launch<7>(bwd, a, blocks, st)); break;
+            default: YB_LAUNCH(name, st, decode_rows_launch<8>(bwd, a, blocks, st)); break;
+        }
+        return 0;
+    }
     if (bwd) YB_LAUNCH("decode_bwd_kernel", st, decode_kernel<true><<<blocks, threads, 0, st>>>(a));
     else     YB_LAUNCH("decode_fwd_kernel", st, decode_kernel<false><<<blocks, threads, 0, st>>>(a));
     return 0;

@@ -49,6 +49,7 @@ struct FilterArgs {
     int* tile_counts;          // (B, tiles_per_img)      (NCHW two-launch path)
     unsigned long long* lb_state;  // (B, groups_per_img): flag << 32 | value, zeroed before the launch
     unsigned int* lb_ticket;       // (B): next group id of every image
+    unsigned int* lb_seen;         // [2]: rows / candidates of the groups that have finished their objectness pass
     float4* boxes;
     float* scores;
     int64_t* classes;
@@ -182,19 +183,70 @@ __device__ __forceinline__ int lb_exclusive(const unsigned long long* st, int g,
     return prefix;
 }
 
+// One candidate row -> (box, score, class) at output slot `o` (train.py:1154-1216).  X(c) loads channel c of the row.
+template <typename Load>
+__device__ __forceinline__ void filter_emit_row(const FilterArgs& a, const FilterScale& L, uint32_t r, size_t o, Load X,
+                                                float inv_s, float pt, float pl) {
+    uint32_t cell, an, gy, gx;
+    L.d_A.divmod(r, cell, an);
+    L.d_W.divmod(cell, gy, gx);
+    const float aw = __ldg(L.anchors + an * 2), ah = __ldg(L.anchors + an * 2 + 1);
+    const float x0 = X(0), x1r = X(1), x2r = X(2), x3r = X(3), x4r = X(4);
+    float cprob;
+    int cid;
+    class_max(a.nc, [&](int cc) { return X(5 + cc); }, cprob, cid);
+    // decode (:1154) with the model's img_size
+    const float bx = decode_xy(x0, (float)gx, L.inv_w);
+    const float by = decode_xy(x1r, (float)gy, L.inv_h);
+    const float bw = decode_wh(x2r, aw, a.inv_img);
+    const float bh = decode_wh(x3r, ah, a.inv_img);
+    // pixels, corners, letterbox reverse (:1192-1213)
+    const float xc = bx * a.img, yc = by * a.img, wp = bw * a.img, hp = bh * a.img;
+    float x1 = xc - wp * 0.5f, y1 = yc - hp * 0.5f, x2 = xc + wp * 0.5f, y2 = yc + hp * 0.5f;
+    if (a.letterbox) {
+        x1 = (x1 - pl) * inv_s; y1 = (y1 - pt) * inv_s;
+        x2 = (x2 - pl) * inv_s; y2 = (y2 - pt) * inv_s;
+    }
+    a.boxes[o] = make_float4(x1, y1, x2, y2);
+    a.scores[o] = sigmoidf_ref(x4r) * cprob;  // :1216
+    a.classes[o] = (int64_t)cid;
+}
+
+// LONG = false: rows of at most 12 floats; the whole group (8 tiles, <= 48 KB) is staged by one bulk copy issued
+//               before anything else — the objectness column touches every sector of such rows anyway — and both
+//               phases read shared memory.
+// LONG = true:  longer rows (nc = 80: 340 bytes).  Phase A reads the objectness column with strided loads (one
+//               128-byte line per row), the group still spans 8 tiles so that only ~25 groups per image take part in
+//               the look-back (with one tile per group the look-back's L2 round trips, ~200 participants per image,
+//               cost more than the data: 180 us instead of the ~95 us the bytes need).  Phase B first emits the
+//               candidates of sparse tiles straight from global memory (no barrier in between: with a barrier per
+//               tile the two or three threads that own a candidate stall the whole CTA for ~6 us of dependent
+//               loads per tile), then streams the dense tiles (a quarter of the rows or more pass) through ONE
+//               shared-memory tile buffer, so that five CTAs per SM keep >200 KB of bulk copies in flight.  When the
+//               batch has been dense so far (lb_seen) the first copy starts before phase A.
+template <bool LONG>
 __global__ void __launch_bounds__(kFTile) filter_onepass_kernel(const FilterArgs a) {
     extern __shared__ __align__(128) float s_tile[];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_wcnt[kFMaxGroup][kFTile / 32];
-    __shared__ int s_prefix, s_total;
+    __shared__ int s_prefix, s_hint;
     __shared__ unsigned s_gid;
     // row ids (within the group) of the passing rows, in row order, live behind the staged rows
     unsigned short* s_list = reinterpret_cast<unsigned short*>(s_tile + a.sobj_offset);
     const uint32_t b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
         s_gid = atomicAdd(a.lb_ticket + b, 1u);   // the g-th CTA of the image to start owns group g
+        // density hint for long rows: rows and candidates of the groups (of any image) that have finished their
+        // objectness pass so far.  A wrong hint only costs bandwidth, never correctness.
+        int hint = 0;
+        if (LONG && a.stage_ok) {
+            const unsigned rows_done = *(volatile unsigned*)(a.lb_seen), cand_done = *(volatile unsigned*)(a.lb_seen + 1);
+            hint = rows_done != 0u && (unsigned long long)cand_done * 4ull >= (unsigned long long)rows_done;
+        }
+        s_hint = hint;
     }
     __syncthreads();
     const uint32_t group = s_gid;
@@ -208,20 +260,26 @@ __global__ void __launch_bounds__(kFTile) filter_onepass_kernel(const FilterArgs
     const size_t base = ((size_t)b * L.rows + row0) * a.row;  // float offset of the group
     const float* g = L.pred + base;
     unsigned long long* st = a.lb_state + (size_t)b * a.groups_per_img;
+    const uint32_t tile_fl = (uint32_t)kFTile * a.row;        // floats of a full tile
 
-    // rows of at most 32 bytes: the objectness column touches every sector anyway, so the whole group is staged
-    // up front (one bulk copy issued before anything else) and phase A reads shared memory
-    const uint32_t nfl = nrows * a.row;
-    const bool can_bulk = (base & 3) == 0 && (nfl & 3) == 0;
-    const bool early = a.stage_ok && a.row <= 8;
-    if (early) {
-        if (can_bulk) {
-            if (threadIdx.x == 0) bulk_load(s_tile, g, nfl * 4u, &s_bar);
-            mbar_wait(&s_bar, 0);
+    // tile k of the group as a bulk-copy job: rows, floats, source, 16-byte alignment
+    auto tile_rows = [&](int k) { return min((uint32_t)kFTile, nrows - (uint32_t)k * kFTile); };
+    auto tile_bulk_ok = [&](int k) { return ((base + (size_t)k * tile_fl) & 3) == 0 && ((tile_rows(k) * a.row) & 3u) == 0; };
+    int pending = -1;               // tile whose bulk copy is in flight / has landed in the buffer (all threads agree)
+    uint32_t parity = 0u;
+
+    if (!LONG) {   // the whole group up front
+        const uint32_t nfl = nrows * a.row;
+        if ((base & 3) == 0 && (nfl & 3) == 0) {
+            if (threadIdx.x == 0) bulk_load(s_tile, g, nfl * 4u, &s_bar[0]);
+            mbar_wait(&s_bar[0], 0);
         } else {
             for (uint32_t e = threadIdx.x; e < nfl; e += kFTile) s_tile[e] = g[e];
             __syncthreads();
         }
+    } else if (s_hint && tile_bulk_ok(0)) {   // speculative: the first tile
+        if (threadIdx.x == 0) bulk_load(s_tile, g, tile_rows(0) * a.row * 4u, &s_bar[0]);
+        pending = 0;
     }
 
     // phase A: objectness test of this thread's row in every tile of the group (the only pass over the column).
@@ -233,7 +291,7 @@ __global__ void __launch_bounds__(kFTile) filter_onepass_kernel(const FilterArgs
     for (int k = 0; k < kFMaxGroup; ++k) {
         const uint32_t rl = k * kFTile + threadIdx.x;
         xo[k] = __int_as_float(0x7fc00000);   // NaN: fails both quick tests and the exact one
-        if (k < G && rl < nrows) xo[k] = early ? s_tile[rl * a.row + 4] : __ldg(g + (size_t)rl * a.row + 4);
+        if (k < G && rl < nrows) xo[k] = LONG ? __ldg(g + (size_t)rl * a.row + 4) : s_tile[rl * a.row + 4];
     }
     unsigned mybal[kFMaxGroup];
 #pragma unroll
@@ -248,34 +306,37 @@ __global__ void __launch_bounds__(kFTile) filter_onepass_kernel(const FilterArgs
         }
     }
     __syncthreads();
-    // offsets of this warp's rows of tile k in the group's list; the group's total
-    int woff[kFMaxGroup];
+    // offsets of this warp's rows of tile k in the group's list, per-tile counts, the group's total
+    int woff[kFMaxGroup], tcnt[kFMaxGroup];
     int total = 0;
 #pragma unroll
     for (int k = 0; k < kFMaxGroup; ++k) {
         woff[k] = total;
+        tcnt[k] = 0;
         if (k < G) {
 #pragma unroll
             for (int w = 0; w < kFTile / 32; ++w) {
                 const int c = s_wcnt[k][w];
                 if (w < warp) woff[k] += c;
-                total += c;
+                tcnt[k] += c;
             }
+            total += tcnt[k];
         }
     }
     // publish the group's count (the first group's count is its inclusive prefix)
-    if (threadIdx.x == 0) lb_store(st + group, ((group == 0 ? 2ull : 1ull) << 32) | (unsigned)total);
-
-    // dense groups: stage through shared memory while the look-back is in progress
-    const bool staged = early || (a.stage_ok && total * 4 >= (int)nrows);
-    bool bulk = false;
-    if (staged && !early) {
-        bulk = can_bulk;
-        if (bulk) {
-            if (threadIdx.x == 0) bulk_load(s_tile, g, nfl * 4u, &s_bar);
-        } else {
-            for (uint32_t e = threadIdx.x; e < nfl; e += kFTile) s_tile[e] = g[e];
-        }
+    if (threadIdx.x == 0) {
+        lb_store(st + group, ((group == 0 ? 2ull : 1ull) << 32) | (unsigned)total);
+        if (LONG) { atomicAdd(a.lb_seen, nrows); atomicAdd(a.lb_seen + 1, (unsigned)total); }
+    }
+    // LONG: a tile is staged when at least a quarter of its rows pass; start the first one unless a copy is in flight
+    unsigned dense_mask = 0u;
+#pragma unroll
+    for (int k = 0; k < kFMaxGroup; ++k)
+        if (LONG && k < G && a.stage_ok && tcnt[k] > 0 && tcnt[k] * 4 >= (int)tile_rows(k) && tile_bulk_ok(k)) dense_mask |= 1u << k;
+    if (LONG && pending < 0 && dense_mask) {
+        const int k = __ffs(dense_mask) - 1;
+        if (threadIdx.x == 0) bulk_load(s_tile, g + (size_t)k * tile_fl, tile_rows(k) * a.row * 4u, &s_bar[0]);
+        pending = k;
     }
 #pragma unroll
     for (int k = 0; k < kFMaxGroup; ++k)
@@ -293,9 +354,7 @@ __global__ void __launch_bounds__(kFTile) filter_onepass_kernel(const FilterArgs
         }
     }
     __syncthreads();
-    if (total == 0) return;
     const int prefix = s_prefix;
-    if (bulk) mbar_wait(&s_bar, 0);
 
     // phase B: emit, one passing row per thread and step (the list is dense: no idle lanes at any pass rate)
     float inv_s = 1.0f, pt = 0.0f, pl = 0.0f;
@@ -305,42 +364,59 @@ __global__ void __launch_bounds__(kFTile) filter_onepass_kernel(const FilterArgs
         pl = a.letterbox[b * 3 + 2];
     }
     const int n_emit = min(total, a.cap - prefix);
+    if (!LONG) {
+#pragma unroll 1
+        for (int c = threadIdx.x; c < n_emit; c += kFTile) {
+            const uint32_t rl = s_list[c];
+            const float* x = s_tile + rl * a.row;
+            filter_emit_row(a, L, row0 + rl, (size_t)b * a.cap + prefix + c, [&](int ch) { return x[ch]; }, inv_s, pt, pl);
+        }
+        return;
+    }
+    // sparse tiles: straight from global memory, every candidate of the group at once, no barrier
+    if (pending >= 0 && !((dense_mask >> pending) & 1u) && tcnt[pending] > 0) dense_mask |= 1u << pending;   // a speculative copy that is useful after all
 #pragma unroll 1
     for (int c = threadIdx.x; c < n_emit; c += kFTile) {
         const uint32_t rl = s_list[c];
-        const uint32_t r = row0 + rl;
-        uint32_t cell, an, gy, gx;
-        L.d_A.divmod(r, cell, an);
-        L.d_W.divmod(cell, gy, gx);
-        const float aw = __ldg(L.anchors + an * 2), ah = __ldg(L.anchors + an * 2 + 1);
-        float x0, x1r, x2r, x3r, x4r, cprob;
-        int cid;
-        if (staged) {
-            const float* x = s_tile + rl * a.row;
-            x0 = x[0]; x1r = x[1]; x2r = x[2]; x3r = x[3]; x4r = x[4];
-            class_max(a.nc, [&](int cc) { return x[5 + cc]; }, cprob, cid);
-        } else {
-            const float* x = g + (size_t)rl * a.row;
-            x0 = __ldg(x); x1r = __ldg(x + 1); x2r = __ldg(x + 2); x3r = __ldg(x + 3); x4r = __ldg(x + 4);
-            class_max(a.nc, [&](int cc) { return __ldg(x + 5 + cc); }, cprob, cid);
-        }
-        // decode (:1154) with the model's img_size
-        const float bx = decode_xy(x0, (float)gx, L.inv_w);
-        const float by = decode_xy(x1r, (float)gy, L.inv_h);
-        const float bw = decode_wh(x2r, aw, a.inv_img);
-        const float bh = decode_wh(x3r, ah, a.inv_img);
-        // pixels, corners, letterbox reverse (:1192-1213)
-        const float xc = bx * a.img, yc = by * a.img, wp = bw * a.img, hp = bh * a.img;
-        float x1 = xc - wp * 0.5f, y1 = yc - hp * 0.5f, x2 = xc + wp * 0.5f, y2 = yc + hp * 0.5f;
-        if (a.letterbox) {
-            x1 = (x1 - pl) * inv_s; y1 = (y1 - pt) * inv_s;
-            x2 = (x2 - pl) * inv_s; y2 = (y2 - pt) * inv_s;
-        }
-        const size_t o = (size_t)b * a.cap + prefix + c;
-        a.boxes[o] = make_float4(x1, y1, x2, y2);
-        a.scores[o] = sigmoidf_ref(x4r) * cprob;  // :1216
-        a.classes[o] = (int64_t)cid;
+        if ((dense_mask >> (rl / kFTile)) & 1u) continue;
+        const float* x = g + (size_t)rl * a.row;
+        filter_emit_row(a, L, row0 + rl, (size_t)b * a.cap + prefix + c, [&](int ch) { return __ldg(x + ch); }, inv_s, pt, pl);
     }
+    // dense tiles: one bulk copy at a time through the tile buffer
+    int off = 0;   // list offset of tile k
+#pragma unroll 1
+    for (int k = 0; k < G; ++k) {
+        const int n_k = max(0, min(tcnt[k], n_emit - off));
+        if ((dense_mask >> k) & 1u) {
+            if (pending >= 0 && pending != k) {   // a speculative copy of an empty tile: it must land before the next one
+                mbar_wait(&s_bar[0], parity);
+                parity ^= 1u;
+                pending = -1;
+            }
+            if (pending != k) {
+                if (threadIdx.x == 0) bulk_load(s_tile, g + (size_t)k * tile_fl, tile_rows(k) * a.row * 4u, &s_bar[0]);
+            }
+            mbar_wait(&s_bar[0], parity);
+            parity ^= 1u;
+            pending = -1;
+            const float* xb = s_tile - (size_t)k * tile_fl;
+#pragma unroll 1
+            for (int c = threadIdx.x; c < n_k; c += kFTile) {
+                const uint32_t rl = s_list[off + c];
+                const float* x = xb + (size_t)rl * a.row;
+                filter_emit_row(a, L, row0 + rl, (size_t)b * a.cap + prefix + off + c, [&](int ch) { return x[ch]; }, inv_s, pt, pl);
+            }
+            __syncthreads();   // the buffer is free again
+            const unsigned rest = dense_mask >> (k + 1);
+            if (rest) {          // next dense tile: start its copy right away
+                const int k2 = k + __ffs(rest);
+                if (threadIdx.x == 0) bulk_load(s_tile, g + (size_t)k2 * tile_fl, tile_rows(k2) * a.row * 4u, &s_bar[0]);
+                pending = k2;
+            }
+        }
+        off += tcnt[k];
+    }
+    if (pending >= 0) mbar_wait(&s_bar[0], parity);   // a speculative copy nobody needed must still land before the CTA exits
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -490,12 +566,9 @@ static int filter_fill(const yb_heads_desc* d, FilterArgs& a) {
     YB_CHECK_ARG(d->layout == YB_LAYOUT_BHWAC || d->layout == YB_LAYOUT_NCHW, "filter: unknown layout %d", d->layout);
     a.nchw = d->layout == YB_LAYOUT_NCHW ? 1 : 0;
     a.img = d->img_size; a.inv_img = 1.0f / d->img_size;
-    // tiles per CTA: about 44 KB of head rows, at most kFMaxGroup
-    {
-        const size_t tile_bytes = (size_t)kFTile * a.row * sizeof(float);
-        size_t G = (44 * 1024) / tile_bytes;
-        a.G = (int)(G < 1 ? 1 : (G > (size_t)kFMaxGroup ? (size_t)kFMaxGroup : G));
-    }
+    // tiles per CTA: kFMaxGroup in the reference layout (short rows stage the whole group, long rows stream tile by
+    // tile); NCHW keeps its own cell tiling
+    a.G = kFMaxGroup;
     uint32_t tile = 0, group = 0;
     for (int s = 0; s < d->S; ++s) {
         YB_CHECK_ARG(d->H[s] > 0 && d->W[s] > 0, "filter: bad grid at scale %d", s);
@@ -525,7 +598,7 @@ extern "C" size_t yb_filter_workspace_bytes(const yb_heads_desc* d) {
     if (yb::filter_fill(d, a)) return 0;
     // NCHW: per-tile counts (4 B); reference layout: look-back state (8 B per group) + one ticket per image
     const size_t nchw = (size_t)d->B * a.tiles_per_img * sizeof(int);
-    const size_t lb = (size_t)d->B * a.groups_per_img * sizeof(unsigned long long) + (size_t)d->B * sizeof(unsigned int);
+    const size_t lb = (size_t)d->B * a.groups_per_img * sizeof(unsigned long long) + ((size_t)d->B + 2) * sizeof(unsigned int);
     return (nchw > lb ? nchw : lb) + 16;
 }
 
@@ -561,10 +634,12 @@ extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const
     }
     a.tile_counts = reinterpret_cast<int*>(ws);
     a.boxes = reinterpret_cast<float4*>(boxes); a.scores = scores; a.classes = classes; a.counts = counts;
-    size_t smem = (size_t)a.G * kFTile * a.row * sizeof(float);
-    a.stage_ok = smem <= 200 * 1024;
+    const size_t tile_fl = ((size_t)kFTile * a.row + 31) / 32 * 32;
+    const bool long_rows = (size_t)a.G * kFTile * a.row * sizeof(float) > 48 * 1024;
+    size_t smem = long_rows ? tile_fl * sizeof(float) : (size_t)a.G * kFTile * a.row * sizeof(float);
+    a.stage_ok = smem <= 200 * 1024;   // else: rows so long that one tile does not fit; the emit reads global memory
     if (!a.stage_ok) smem = 0;
-    smem = (smem + 15) / 16 * 16;
+    smem = (smem + 127) / 128 * 128;
     a.sobj_offset = (uint32_t)(smem / sizeof(float));
     smem += (size_t)a.G * kFTile * sizeof(float);   // NCHW: sigmoid(obj) scratch; reference layout: u16 row list (half of it)
     cudaStream_t st = (cudaStream_t)stream;
@@ -584,10 +659,17 @@ extern "C" int yb_filter_compact(const yb_heads_desc* d, float conf_thres, const
     dim3 grid(a.groups_per_img, d->B);
     a.lb_state = reinterpret_cast<unsigned long long*>(ws);
     a.lb_ticket = reinterpret_cast<unsigned int*>(a.lb_state + (size_t)d->B * a.groups_per_img);
-    YB_CUDA(cudaMemsetAsync(ws, 0, (size_t)d->B * a.groups_per_img * sizeof(unsigned long long) + (size_t)d->B * sizeof(unsigned int), st));
+    a.lb_seen = a.lb_ticket + d->B;
+    YB_CUDA(cudaMemsetAsync(ws, 0, (size_t)d->B * a.groups_per_img * sizeof(unsigned long long) + ((size_t)d->B + 2) * sizeof(unsigned int), st));
     const size_t dyn = smem;
-    if (dyn > 48 * 1024)
-        YB_CUDA(cudaFuncSetAttribute(filter_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    YB_LAUNCH("filter_onepass_kernel", st, filter_onepass_kernel<<<grid, kFTile, dyn, st>>>(a));
+    if (long_rows) {
+        if (dyn > 48 * 1024)
+            YB_CUDA(cudaFuncSetAttribute(filter_onepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        YB_LAUNCH("filter_onepass_kernel", st, filter_onepass_kernel<true><<<grid, kFTile, dyn, st>>>(a));
+    } else {
+        if (dyn > 48 * 1024)
+            YB_CUDA(cudaFuncSetAttribute(filter_onepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        YB_LAUNCH("filter_onepass_kernel", st, filter_onepass_kernel<false><<<grid, kFTile, dyn, st>>>(a));
+    }
     return 0;
 }

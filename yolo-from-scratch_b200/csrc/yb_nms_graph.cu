@@ -69,7 +69,8 @@ struct GArgs {
     u32 k16x2;      // half2 {K, K}, K = (1+th)/th * (1+2^-6) rounded up, th = thr * (1 - 2^-12)
     int hexp;       // local frames map a row tile's half extent to [2^hexp, 2^(hexp+1))
     long long trick_max_numel;
-    u32 *k0, *v0, *k1, *v1;            // (B,cap) radix ping-pong buffers (ballot score sort of large images only)
+    u32 *k0, *v0;                      // (B,cap) sorted runs (key, index) of large images, merged by graph_score_merge_kernel
+    int n_score_chunks;
     u32* order;                        // (B,cap) score rank -> original index      (score kernel)
     u32* rinv;                         // (B,cap) original index -> score rank      (score kernel)
     u32* pos;                          // (B,cap) position -> original index        (spatial kernel)
@@ -165,39 +166,73 @@ __device__ __forceinline__ u32 spatial_key(const float4 q, const int64_t* classe
 // ------------------------------------------------------------------------------------------------
 // score order: stable descending sort of one image, rank <-> index maps.  Its own launch on a side stream:
 // only the resolve kernel needs it, so it overlaps with the spatial kernel and the edge discovery.
-// SMEM = true: shared-memory blocked sort (cap <= kS16MaxM, 512 threads); false: warp-ballot sort through
-// global ping-pong buffers (any cap, 1024 threads).
+// One CTA per chunk of kScoreChunk candidates: shared-memory blocked radix sort (yb_sort.cuh).  An image that fits
+// one chunk gets its final order here; larger images get sorted runs, merged by graph_score_merge_kernel.
 // ------------------------------------------------------------------------------------------------
-template <int NT, bool SMEM>
-__global__ void __launch_bounds__(NT) graph_score_kernel(const GArgs a) {
-    extern __shared__ __align__(16) u32 s_dyn[];  // SMEM: s16_smem_bytes(cap); else 32*256 + 256 words
-    __shared__ int s_skip;
-    const int b = blockIdx.x, tid = threadIdx.x;
+constexpr int kScoreChunk = 26880;   // == kS16MaxM
+__global__ void __launch_bounds__(kS16Threads) graph_score_kernel(const GArgs a) {
+    extern __shared__ __align__(16) u32 s_dyn[];  // s16_smem_bytes(min(cap, kScoreChunk))
+    const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    constexpr int NT = kS16Threads;
     const size_t off = (size_t)b * a.cap;
     int M = a.counts ? a.counts[b] : a.cap;
     M = M < 0 ? 0 : (M > a.cap ? a.cap : M);
-    if (M == 0) return;
-    const float* scores = a.scores + off;
-    u32* order = a.order + off;
-    u32* rinv = a.rinv + off;
-    if (SMEM) {
-        const u32* res = s16_sort(M, a.cap, [&](int i) { return desc_key(scores[i]); }, s_dyn);
-        for (int r = tid; r < M; r += NT) {
+    const int c0 = chunk * kScoreChunk;
+    const int Mc = min(M - c0, kScoreChunk);
+    if (Mc <= 0) return;
+    const float* scores = a.scores + off + c0;
+    const u32* res = s16_sort(Mc, min(a.cap, kScoreChunk), [&](int i) { return desc_key(scores[i]); }, s_dyn);
+    if (a.n_score_chunks == 1) {   // the whole image: final order
+        u32* order = a.order + off;
+        u32* rinv = a.rinv + off;
+        for (int r = tid; r < Mc; r += NT) {
             const u32 idx = res[r] >> 16;
             order[r] = idx;
             rinv[idx] = (u32)r;
         }
-    } else {
-        u32 *ka = a.k0 + off, *va = a.v0 + off, *kb = a.k1 + off, *vb = a.v1 + off;
-        for (int i = tid; i < M; i += NT) { ka[i] = desc_key(scores[i]); va[i] = (u32)i; }
-        __syncthreads();
-        radix_sort(ka, va, kb, vb, M, 0, 32, s_dyn, s_dyn + 32 * 256, &s_skip);
-        for (int r = tid; r < M; r += NT) {
-            const u32 idx = va[r];
-            order[r] = idx;
-            rinv[idx] = (u32)r;
+    } else {                       // a sorted run for graph_score_merge_kernel
+        u32* ckey = a.k0 + off + c0;
+        u32* cidx = a.v0 + off + c0;
+        for (int r = tid; r < Mc; r += NT) {
+            const u32 idx = res[r] >> 16;
+            ckey[r] = desc_key(scores[idx]);
+            cidx[r] = (u32)c0 + idx;
         }
     }
+}
+
+// Large images (more candidates than one shared-memory sort holds, e.g. 100,800 at 1280^2): the runs of
+// graph_score_kernel are merged by ranking.  A thread takes one element of one run; its final rank is its position
+// in its own run plus, for every other run, the number of elements that go before it — upper bound in the runs of
+// lower indices (they win ties: stable), lower bound in the runs of higher indices.  Neighbouring threads search
+// neighbouring keys, so the binary searches stay in cache.
+__global__ void __launch_bounds__(256) graph_score_merge_kernel(const GArgs a) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const size_t off = (size_t)b * a.cap;
+    int M = a.counts ? a.counts[b] : a.cap;
+    M = M < 0 ? 0 : (M > a.cap ? a.cap : M);
+    if (p >= M) return;
+    const u32* ckey = a.k0 + off;
+    const u32 key = ckey[p];
+    const int c = p / kScoreChunk;
+    u32 rank = (u32)(p - c * kScoreChunk);
+    for (int o = 0; o * kScoreChunk < M; ++o) {
+        if (o == c) continue;
+        const u32* run = ckey + (size_t)o * kScoreChunk;
+        const int len = min(kScoreChunk, M - o * kScoreChunk);
+        int lo = 0, hi = len;   // first position whose key is > key (o < c) or >= key (o > c)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const u32 k = run[mid];
+            const bool before = o < c ? k <= key : k < key;
+            if (before) lo = mid + 1; else hi = mid;
+        }
+        rank += (u32)lo;
+    }
+    const u32 idx = a.v0[off + p];
+    a.order[off + rank] = idx;
+    a.rinv[off + idx] = rank;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -704,7 +739,6 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         const float t2 = info.t2;
         const float t3 = a.t3;
         const bool class_mode = info.mode == G_CLASS;
-        const bool class_sorted = class_mode && a.n_chunks == 1;   // one chunk: tiles are ordered by class
 
         // ---- the tile's local frame ----
         const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
@@ -759,7 +793,24 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         int n_buf = 0;   // edges waiting in w.ebuf
         int n_cand = 0;  // filter survivors waiting in w.cand
 
+        // Tiles are walked chunk by chunk (one chunk at 640^2).  Inside a chunk the tiles are ordered by class in
+        // per-class mode, so the walk enters a chunk at the first tile that can hold icmin (32-way probe) and
+        // leaves it when every lane is past icmax.
+        constexpr int kCT = kChunk / kTile;
+        int chunk_end = min(info.n_tiles, (I / kCT + 1) * kCT);
         for (int J0 = I;; J0 += 32) {
+            if (J0 >= chunk_end && chunk_end < info.n_tiles) {   // enter the next chunk
+                J0 = chunk_end;
+                chunk_end = min(info.n_tiles, chunk_end + kCT);
+                if (class_mode) {
+                    const int step = (chunk_end - J0 + 31) / 32;
+                    const int Jp = J0 + lane * step;
+                    const bool ge = Jp < chunk_end && __float_as_uint(ts[Jp * 2 + 1].w) >= icmin;   // class max: non-decreasing
+                    const unsigned m = __ballot_sync(0xffffffffu, ge);
+                    const int first = m ? __ffs(m) - 1 : 32;
+                    J0 += max(first - 1, 0) * step;   // everything before the last probe below icmin is below icmin
+                }
+            }
             const bool tail = J0 >= info.n_tiles;  // one extra round flushes the last partial chunk
             int n_t = 0;
             int n_tail = kSlots;   // valid slots of the chunk about to be processed (< kSlots only in the tail)
@@ -772,15 +823,15 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
             } else {
                 // level 1: lane <-> tile J
                 const int Jl = J0 + lane;
-                bool ok = Jl < info.n_tiles;
+                bool ok = Jl < chunk_end;
                 float4 jb = make_float4(0.f, 0.f, 0.f, 0.f), ja = jb;
                 if (ok) { jb = ts[Jl * 2]; ja = ts[Jl * 2 + 1]; }
                 if (class_mode) {
-                    const bool beyond = ok && __float_as_uint(ja.z) > icmax;
+                    const bool beyond = !ok || __float_as_uint(ja.z) > icmax;
                     ok = ok && !beyond && __float_as_uint(ja.w) >= icmin;
-                    // tiles ordered by class (single chunk): nothing beyond the last tile that can hold icmax
-                    if (class_sorted && __ballot_sync(0xffffffffu, beyond) == 0xffffffffu) {
-                        J0 = info.n_tiles - 32;  // next round is the tail
+                    // the chunk's tiles are ordered by class: nothing beyond the last tile that can hold icmax
+                    if (__ballot_sync(0xffffffffu, beyond) == 0xffffffffu) {
+                        J0 = chunk_end - 32;  // next round: the next chunk, or the tail
                         continue;
                     }
                 }
@@ -1096,7 +1147,7 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
 
 // ---- host side -------------------------------------------------------------------------------
 struct GLayout {
-    size_t k[4], order, rinv, pos, sboxes, skey, sidx, scls, tstat, sstat, info, iflags, ticket, edges, total;
+    size_t k[2], order, rinv, pos, sboxes, skey, sidx, scls, tstat, sstat, info, iflags, ticket, edges, total;
 };
 
 static inline size_t g_align(size_t x) { return (x + 255) / 256 * 256; }
@@ -1106,8 +1157,8 @@ static GLayout graph_layout(int B, int cap) {
     size_t o = 0;
     const size_t n = (size_t)B * cap;
     const size_t tcap = ((size_t)cap + kTile - 1) / kTile;
-    const size_t nk = cap > kS16MaxM ? n : 0;   // ping-pong buffers: only the ballot score sort of large images
-    for (int i = 0; i < 4; ++i) { L.k[i] = o; o = g_align(o + nk * 4); }
+    const size_t nk = cap > kS16MaxM ? n : 0;   // sorted runs: only images larger than one shared-memory sort
+    for (int i = 0; i < 2; ++i) { L.k[i] = o; o = g_align(o + nk * 4); }
     L.order = o; o = g_align(o + n * 4);
     L.rinv = o; o = g_align(o + n * 4);
     L.pos = o; o = g_align(o + n * 4);
@@ -1180,7 +1231,8 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
         a.hexp = a.thr >= 0.35f ? 5 : (a.thr >= 0.1f ? 4 : 3);   // keeps K * (row area) inside the half range
     }
     a.trick_max_numel = trick_max_numel;
-    a.k0 = (u32*)(w + L.k[0]); a.v0 = (u32*)(w + L.k[1]); a.k1 = (u32*)(w + L.k[2]); a.v1 = (u32*)(w + L.k[3]);
+    a.k0 = (u32*)(w + L.k[0]); a.v0 = (u32*)(w + L.k[1]);
+    a.n_score_chunks = (cap + kScoreChunk - 1) / kScoreChunk;
     a.order = (u32*)(w + L.order); a.rinv = (u32*)(w + L.rinv); a.pos = (u32*)(w + L.pos);
     a.sboxes = (float4*)(w + L.sboxes); a.skey = (u32*)(w + L.skey); a.sidx = (u32*)(w + L.sidx); a.scls = (u32*)(w + L.scls);
     a.tstat = (float4*)(w + L.tstat);
@@ -1202,14 +1254,14 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
         YB_CUDA(cudaStreamWaitEvent(fj->side, fj->fork[slot], 0));
         ss = fj->side;
     }
-    if (cap <= kS16MaxM) {
-        const size_t sort_smem = s16_smem_bytes(cap);
-        YB_CUDA(cudaFuncSetAttribute(graph_score_kernel<kS16Threads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sort_smem));
-        YB_LAUNCH("graph_score_kernel", ss, (graph_score_kernel<kS16Threads, true><<<B, kS16Threads, sort_smem, ss>>>(a)));
-    } else {
-        const size_t sort_smem = (32 * 256 + 256) * sizeof(u32);
-        YB_LAUNCH("graph_score_kernel", ss, (graph_score_kernel<kSortThreads, false><<<B, kSortThreads, sort_smem, ss>>>(a)));
+    {
+        const size_t sort_smem = s16_smem_bytes(cap < kScoreChunk ? cap : kScoreChunk);
+        YB_CUDA(cudaFuncSetAttribute(graph_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+        YB_LAUNCH("graph_score_kernel", ss,
+                  (graph_score_kernel<<<dim3(a.n_score_chunks, B), kS16Threads, sort_smem, ss>>>(a)));
+        if (a.n_score_chunks > 1)
+            YB_LAUNCH("graph_score_merge_kernel", ss,
+                      (graph_score_merge_kernel<<<dim3((cap + 255) / 256, B), 256, 0, ss>>>(a)));
     }
     if (fj) YB_CUDA(cudaEventRecord(fj->join[slot], fj->side));
 
