@@ -44,6 +44,10 @@ constexpr int kSubs = kTile / kSub;
 constexpr uint32_t kNoSub = 0xffffffffu;
 constexpr int kGatherThreads = 256;
 constexpr int kEdgeThreads = 256;
+#ifndef YB_EDGE_CTAS
+#define YB_EDGE_CTAS 4
+#endif
+constexpr int kEdgeCtasPerSM = YB_EDGE_CTAS;
 constexpr int kResolveThreads = 1024;
 
 enum { G_PLAIN = 0, G_TRICK = 1, G_CLASS = 2 };
@@ -555,17 +559,20 @@ __device__ __forceinline__ void edge_flush(const GArgs& a, EdgeWarp& w, int b, u
 
 // Exact stage: the queued (row, column) pairs, one per lane.  torchvision's predicate with the division-free
 // margin test; ambiguous lanes redo the exact fma/div arithmetic with the higher-scored box as `a`.
-__device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I,
-                                          const float4* __restrict__ sb, const u32* __restrict__ skey,
-                                          const u32* __restrict__ sidx, const u32* __restrict__ scls,
-                                          uint2* __restrict__ edges, int& n_cand, int& n_buf) {
+__device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const int M, const bool class_mode, int b, int I,
+                                          int& n_cand, int& n_buf) {
+    // (rare path: the pointers are rebuilt here instead of being kept in registers through the hot loops)
+    const size_t off = (size_t)b * a.cap;
+    const float4* __restrict__ sb = a.sboxes + (size_t)b * a.scap;
+    const u32* __restrict__ skey = a.skey + off;
+    const u32* __restrict__ sidx = a.sidx + off;
+    const u32* __restrict__ scls = a.scls + off;
+    uint2* __restrict__ edges = a.edges + (u64)b * a.edges_per_img;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float kEps = 9.5367431640625e-07f;     // 2^-20
     const float kTiny = 7.888609052210118e-31f;  // 2^-100
     const float thr = a.thr;
-    const bool class_mode = info.mode == G_CLASS;
-    const int M = info.M;
     __syncwarp();
     for (int k0 = 0; k0 < n_cand; k0 += 32) {
         const int k = k0 + lane;
@@ -619,13 +626,12 @@ __device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const 
 // Lane l stages columns 2*(l&3), +1 of slot l>>2 as one packed record.  Rows are culled against each slot's
 // statistics (one half2 step per dimension pair), the surviving (row, slot) items are packed, and every
 // iteration of the pair loop filters 8 items x 8 columns: 64 pairs on 32 lanes whatever the culling pattern.
-__device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GImg& info, int b, int I, int head,
-                                           const float4* __restrict__ sb, const u32* __restrict__ skey,
-                                           const u32* __restrict__ sidx, const u32* __restrict__ scls,
-                                           uint2* __restrict__ edges, const Frame& f,
-                                           const int n_slots, const bool rvalid, const u32 r_lo, const u32 r_hi,
-                                           const u32 r_wh_t, const u32 r_ar, u32& n_evals, u32& n_cands,
-                                           int& n_cand, int& n_buf) {
+// FULL: all 8 slots are valid (every chunk but the last one of a row tile).
+template <bool FULL>
+__device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const int M, const bool class_mode, int b, int I,
+                                           int head, const float4* __restrict__ sb, const Frame& f, const int n_slots,
+                                           const u32 r_lo, const u32 r_hi, const u32 r_wh_t, const u32 r_ar,
+                                           u32& n_evals, u32& n_cands, int& n_cand, int& n_buf) {
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 2, j = lane & 3;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -637,7 +643,7 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
         const u32 e = sub[grp];
         uint4 box = make_uint4(0x63d063d0u, 0x63d063d0u, 0xe3d0e3d0u, 0xe3d0e3d0u);   // +1000 | -1000: overlaps nothing
         u32 area = 0x3c003c00u;                                                          // 1.0
-        if (e != kNoSub) {
+        if (FULL || e != kNoSub) {
             const float4* src = sb + (size_t)e * kSub + 2 * j;
             const float4 q0 = src[0], q1 = src[1];
             box.x = pack2(h_dn(__fmaf_rd(q0.x, f.S, f.nox)), h_dn(__fmaf_rd(q1.x, f.S, f.nox)));
@@ -651,15 +657,16 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
         c.area = area;
     }
 
-    // ---- row culling against the statistics of each slot; pack the surviving (row, slot) items ----
+    // ---- row culling against the statistics of each slot; pack the surviving (row, slot) items.  Rows beyond
+    //      the image carry +-1000 sentinels in r_lo / r_hi / r_wh_t and never pass. ----
     int n_items = 0;
     const unsigned short my_row = (unsigned short)(lane * (int)sizeof(Rec16));
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
-        if (s < n_slots) {   // warp-uniform: the valid slots of a chunk are a prefix
+        if (FULL || s < n_slots) {   // warp-uniform: the valid slots of a chunk are a prefix
             const uint2 sbx = w.sbx[head + s];
             const __half2 o = __hsub2(__hmin2(as_h2(r_hi), as_h2(sbx.y)), __hmax2(as_h2(r_lo), as_h2(sbx.x)));
-            const bool rok = rvalid & h2_all_ge(as_u32(o), r_wh_t) & h2_all_ge(w.sar[head + s], r_ar);
+            const bool rok = h2_all_ge(as_u32(o), r_wh_t) & h2_all_ge(w.sar[head + s], r_ar);
             const unsigned m = __ballot_sync(0xffffffffu, rok);
             if (rok) {
                 const int at = n_items + __popc(m & lt_mask);
@@ -693,26 +700,28 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const GI
         const __half2 sum = __hadd2(as_h2(rr->area), as_h2(cc->area));
         const u32 x = as_u32(__hfma2(__hmul2(iw, ih), K, __hneg2(sum)));
         if (!__any_sync(0xffffffffu, h2_any_ge0(x))) continue;   // NaN (no overlap at all) is not a candidate
-        // queue the candidates (two ballots: first and second column of every lane)
-        const u32 hit = h2_ge0_bits(x);
+        // queue the candidates: (row, first column of the hit) in one ballot; a lane whose two columns both hit
+        // (rare) queues the second one in another round
+        const u32 hit = ro < (u32)(kTile * sizeof(Rec16)) ? h2_ge0_bits(x) : 0u;   // padding items never
         const u32 i = ro / (u32)sizeof(Rec16);
         const u32 qp = sub[co / (u32)(4 * sizeof(Rec16))] * kSub + 2 * j;
-        const bool c0 = (hit & 1u) && i < kTile;
-        const bool c1 = (hit & 2u) && i < kTile;
-        const unsigned m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
-        if (c0) w.cand[n_cand + __popc(m0 & lt_mask)] = (i << 24) | qp;
+        const unsigned m0 = __ballot_sync(0xffffffffu, hit != 0u);
+        if (hit) w.cand[n_cand + __popc(m0 & lt_mask)] = (i << 24) | (qp + (hit == 2u ? 1u : 0u));
         n_cand += __popc(m0);
-        if (c1) w.cand[n_cand + __popc(m1 & lt_mask)] = (i << 24) | (qp + 1u);
-        n_cand += __popc(m1);
+        const unsigned m1 = __ballot_sync(0xffffffffu, hit == 3u);
+        if (m1) {
+            if (hit == 3u) w.cand[n_cand + __popc(m1 & lt_mask)] = (i << 24) | (qp + 1u);
+            n_cand += __popc(m1);
+        }
         if (n_cand >= kTile) {
             n_cands += (u32)n_cand;
-            cand_process(a, w, info, b, I, sb, skey, sidx, scls, edges, n_cand, n_buf);
+            cand_process(a, w, M, class_mode, b, I, n_cand, n_buf);
         }
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs a) {
+__global__ void __launch_bounds__(kEdgeThreads, kEdgeCtasPerSM) graph_edge_kernel(const GArgs a) {
     __shared__ __align__(16) EdgeWarp s_w[kEdgeThreads / 32];
     const int lane = threadIdx.x & 31;
     EdgeWarp& w = s_w[threadIdx.x >> 5];
@@ -728,14 +737,9 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         const GImg info = a.info[b];
         if (I >= info.n_tiles || a.iflags[b]) continue;
         const int M = info.M;
-        const size_t off = (size_t)b * a.cap;
         const float4* sb = a.sboxes + (size_t)b * a.scap;
-        const u32* skey = a.skey + off;
-        const u32* sidx = a.sidx + off;
-        const u32* scls = a.scls + off;
         const float4* ts = a.tstat + (size_t)b * a.tcap * 2;
         const float4* ss = a.sstat + (size_t)b * a.tcap * kSubs * 2;
-        uint2* edges = a.edges + (u64)b * a.edges_per_img;
         const float t2 = info.t2;
         const float t3 = a.t3;
         const bool class_mode = info.mode == G_CLASS;
@@ -878,9 +882,15 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
                 }
                 // level 3: chunks of 8 sub-tiles
                 int head = 0;
-                for (; n_q - head >= kSlots; head += kSlots)
-                    edge_chunk(a, w, info, b, I, head, sb, skey, sidx, scls, edges, f, n_tail, rvalid, r_lo, r_hi, r_wh_t, r_ar,
-                               n_evals, n_cands, n_cand, n_buf);
+                if (n_tail == kSlots) {
+                    for (; n_q - head >= kSlots; head += kSlots)
+                        edge_chunk<true>(a, w, M, class_mode, b, I, head, sb, f, kSlots, r_lo, r_hi, r_wh_t, r_ar, n_evals,
+                                         n_cands, n_cand, n_buf);
+                } else {   // the last, partial chunk of the row tile
+                    edge_chunk<false>(a, w, M, class_mode, b, I, 0, sb, f, n_tail, r_lo, r_hi, r_wh_t, r_ar, n_evals, n_cands,
+                                      n_cand, n_buf);
+                    head = kSlots;
+                }
                 if (head) {  // move the < 8 leftovers to the front
                     const int rem = n_q - head;
                     u32 v = 0u, va = 0u;
@@ -896,9 +906,9 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) graph_edge_kernel(const GArgs
         }
         if (n_cand) {
             n_cands += (u32)n_cand;
-            cand_process(a, w, info, b, I, sb, skey, sidx, scls, edges, n_cand, n_buf);
+            cand_process(a, w, M, class_mode, b, I, n_cand, n_buf);
         }
-        edge_flush(a, w, b, edges, n_buf);
+        edge_flush(a, w, b, a.edges + (u64)b * a.edges_per_img, n_buf);
         if (lane == 0 && n_evals) {
             atomicAdd(&a.info[b].n_evals, (unsigned long long)n_evals);
             atomicAdd(&a.info[b].n_cands, (unsigned long long)n_cands);
@@ -1274,7 +1284,7 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     }
     const dim3 ggrid((a.tcap + kGatherThreads / 32 - 1) / (kGatherThreads / 32), B);
     YB_LAUNCH("graph_gather_kernel", st, graph_gather_kernel<<<ggrid, kGatherThreads, 0, st>>>(a));
-    const int ctas = sm_count() * 4;  // 4 resident CTAs per SM (launch bounds)
+    const int ctas = sm_count() * kEdgeCtasPerSM;  // resident CTAs per SM (launch bounds)
     YB_LAUNCH("graph_edge_kernel", st, graph_edge_kernel<<<ctas, kEdgeThreads, 0, st>>>(a));
 
     // ---- join, resolve ----
