@@ -84,6 +84,7 @@ struct GArgs {
     u32* scls;                         // (B,cap) position -> class id (per-class mode)
     int* iflags;                       // (B) per-image flags ORed by the chunks of the spatial kernel (zeroed per call)
     int n_chunks;                      // spatial chunks per image
+    u32 resolve_smem_edges;            // edges per image the resolve kernel can hold in shared memory
     float4* tstat;                     // (B,tcap,2) tile bbox | {amin, amax, cmin, cmax}
     float4* sstat;                     // (B,tcap,kSubs,2) sub-tile bbox | {amin, amax, -, -}
     GImg* info;
@@ -1088,13 +1089,31 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
         U[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
         K[w] = 0u; fK[w] = 0u; fU[w] = 0u;
     }
-    uint2* edges = a.edges + (u64)b * a.edges_per_img;
+    uint2* gedges = a.edges + (u64)b * a.edges_per_img;
     const u32 E = info.n_edges;
-    {   // the edge kernel recorded ORIGINAL indices (it does not wait for the score sort): to score ranks, once
+    // The edge kernel recorded ORIGINAL indices (it does not wait for the score sort): to score ranks, once — and,
+    // when the list fits, into shared memory, so that the rounds below never touch global memory.
+    uint2* sedges = reinterpret_cast<uint2*>(s_bits + 4 * nw_cap);   // 16-byte aligned: 4 * nw_cap words
+    const uint2* edges = E <= a.resolve_smem_edges ? sedges : gedges;
+    {
         const u32* __restrict__ rinv = a.rinv + (size_t)b * a.cap;
-        for (u32 e = tid; e < E; e += kResolveThreads) {
-            const uint2 sd = edges[e];
-            edges[e] = make_uint2(rinv[sd.x], rinv[sd.y]);
+        uint2* dst = E <= a.resolve_smem_edges ? sedges : gedges;
+        // four edges per thread and step: the loads of a step are independent (12 in flight per thread)
+        for (u32 e0 = tid; e0 < E; e0 += 4 * kResolveThreads) {
+            uint2 sd[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u32 e = e0 + k * kResolveThreads;
+                sd[k] = e < E ? gedges[e] : make_uint2(0u, 0u);
+            }
+            u32 rx[4], ry[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { rx[k] = rinv[sd[k].x]; ry[k] = rinv[sd[k].y]; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u32 e = e0 + k * kResolveThreads;
+                if (e < E) dst[e] = make_uint2(rx[k], ry[k]);
+            }
         }
     }
     __syncthreads();
@@ -1148,9 +1167,21 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
         base += __popc(K[w]);
     }
     __syncthreads();
-    for (int r = tid; r < M; r += kResolveThreads) {
-        const u32 bits = K[r >> 5];
-        if ((bits >> (r & 31)) & 1u) keep[fK[r >> 5] + __popc(bits & ((1u << (r & 31)) - 1u))] = (int64_t)order[r];
+    for (int r0 = tid; r0 < M; r0 += 4 * kResolveThreads) {   // four independent loads of `order` per step
+        u32 idx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + k * kResolveThreads;
+            idx[k] = r < M ? order[r] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + k * kResolveThreads;
+            if (r < M) {
+                const u32 bits = K[r >> 5];
+                if ((bits >> (r & 31)) & 1u) keep[fK[r >> 5] + __popc(bits & ((1u << (r & 31)) - 1u))] = (int64_t)idx[k];
+            }
+        }
     }
     if (tid == 0) a.n_keep[b] = (int)total;
 }
@@ -1290,9 +1321,11 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     // ---- join, resolve ----
     if (fj) YB_CUDA(cudaStreamWaitEvent(st, fj->join[slot], 0));
     static_assert(kResolveThreads == 2 * kGreedyT, "greedy_resolve splits the CTA in two halves");
-    size_t dyn = (size_t)((cap + 31) / 32) * 4 * 4;
+    const size_t bits_bytes = ((size_t)((cap + 31) / 32) * 4 + 2) * 4;
+    YB_CHECK_ARG(bits_bytes <= 150 * 1024, "nms(graph): cap too large for the resolve kernel");
+    size_t dyn = 160 * 1024;                      // bitmaps + as many edges as fit (20 K per image at 640^2)
+    a.resolve_smem_edges = (u32)((dyn - bits_bytes) / 8);
     if (dyn < sizeof(GreedySmem)) dyn = sizeof(GreedySmem);
-    YB_CHECK_ARG(dyn <= 200 * 1024, "nms(graph): cap too large for the resolve kernel");
     YB_CUDA(cudaFuncSetAttribute(graph_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     YB_LAUNCH("graph_resolve_kernel", st, graph_resolve_kernel<<<B, kResolveThreads, dyn, st>>>(a));
     return 0;
