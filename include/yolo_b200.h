@@ -10,7 +10,11 @@
  *   - every pointer is a CALLER-OWNED DEVICE pointer unless the name ends in `_host`;
  *     the library never allocates, frees or retains memory;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
- *     stream); no entry point synchronises the device or the stream;
+ *     stream); no entry point synchronises the device or the stream.  One entry point,
+ *     yb_batched_nms with YB_NMS_GRAPH, additionally uses a library-owned side stream between two
+ *     events (fork after the work already enqueued on `stream`, join before its last kernel): its
+ *     score sort overlaps with the rest; every result is still ordered after `stream`, and under
+ *     stream capture the fork/join becomes two parallel branches of the captured graph;
  *   - return value 0 = success, otherwise a cudaError_t or a negative YB_E* code;
  *     yb_last_error() returns a thread-local, human readable message for the last failure;
  *   - head tensors use the model-output layout of train.py:608-609: contiguous fp32
@@ -168,6 +172,8 @@ int yb_build_targets(const double* labels, const int* n_gt, const double* letter
  *     class prob/id = max sigmoid(cls) (first max; nc==1: slot 5, id 0)  (:1184-1189)
  *     xyxy in pixels, minus (pad_left,pad_top), divided by scale  (:1192-1213)
  *     score = sigmoid(obj) * class prob  (:1216)
+ *   One pass over the heads (decoupled look-back over groups of 1,024 rows; the workspace is zeroed by a
+ *   memset node of the same call).
  *   Output is per image, order preserving, with a fixed stride of `cap` candidates per image:
  *     boxes (B,cap,4) fp32, scores (B,cap) fp32, classes (B,cap) int64, counts (B) int32.
  *   letterbox (B,3) fp32 = [scale, pad_top, pad_left], NULL = identity.
