@@ -62,6 +62,10 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
         float4 g = BWD ? __ldcs(g4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t r, c;
         a.d_row.divmod(v * 4u, r, c);
+        if (c >= 4u && c + 3u < a.row) {   // four logits of one row (81 of 85 floats at nc=80): a straight copy
+            __stcs(out4 + v, BWD ? g : x);
+            continue;
+        }
         float xs[4] = {x.x, x.y, x.z, x.w};
         float gs[4] = {g.x, g.y, g.z, g.w};
         float o[4];

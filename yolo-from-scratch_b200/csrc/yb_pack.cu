@@ -11,24 +11,30 @@ __global__ void __launch_bounds__(256) pack_kernel(const float4* __restrict__ bo
                                                    float* __restrict__ out, int* __restrict__ offsets) {
     __shared__ int s_base;
     const int b = blockIdx.y;
-    if (threadIdx.x == 0) {
-        int base = 0;
-        for (int i = 0; i < b; ++i) base += max(n_keep[i], 0);
-        s_base = base;
-        if (blockIdx.x == 0) {
-            offsets[b] = base;
-            if (b == B - 1) {
+    const int mine = n_keep[b];
+    if ((int)(blockIdx.x * blockDim.x) >= mine && !(blockIdx.x == 0)) return;   // nothing to pack in this CTA
+    if (threadIdx.x < 32) {   // first row of image b = sum of the earlier images' counts: one warp, coalesced loads
+        int base = 0, failed = 0;
+        for (int i = threadIdx.x; i < B; i += 32) {
+            const int n = n_keep[i];
+            failed |= n < 0;
+            if (i < b) base += max(n, 0);
+        }
+        base = __reduce_add_sync(0xffffffffu, base);
+        failed = __reduce_or_sync(0xffffffffu, failed);
+        if (threadIdx.x == 0) {
+            s_base = base;
+            if (blockIdx.x == 0) {
+                offsets[b] = base;
                 // an image NMS gave up on (n_keep < 0: the bitmask algorithm with too small a workspace) must not
                 // read as "no detections": the total becomes -1 and the host raises at its synchronisation point
-                bool failed = false;
-                for (int i = 0; i < B; ++i) failed |= n_keep[i] < 0;
-                offsets[B] = failed ? -1 : base + max(n_keep[b], 0);
+                if (b == B - 1) offsets[B] = failed ? -1 : base + max(mine, 0);
             }
         }
     }
     __syncthreads();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_keep[b]) return;
+    if (k >= mine) return;
     const size_t src = (size_t)b * cap + (size_t)keep[(size_t)b * cap + k];
     const float4 q = boxes[src];
     float* o = out + (size_t)(s_base + k) * 6;
