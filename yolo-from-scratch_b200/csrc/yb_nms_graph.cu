@@ -80,7 +80,6 @@ struct GArgs {
     u32* pos;                          // (B,cap) position -> original index        (spatial kernel)
     float4* sboxes;                    // (B,scap) boxes in position order (offset applied)
     u32* skey;                         // (B,cap) position -> descending-score key (ties: lower original index first)
-    u32* sidx;                         // (B,cap) position -> original index
     u32* scls;                         // (B,cap) position -> class id (per-class mode)
     int* iflags;                       // (B) per-image flags ORed by the chunks of the spatial kernel (zeroed per call)
     int n_chunks;                      // spatial chunks per image
@@ -439,8 +438,7 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
         const u32 cls = (info.mode == G_CLASS) ? c : 0u;
         sbo[p] = q;
         a.skey[off + p] = desc_key(sc);
-        a.sidx[off + p] = idx;
-        a.scls[off + p] = cls;
+        if (info.mode == G_CLASS) a.scls[off + p] = cls;   // read only in per-class mode
         x1 = f2ord(q.x); y1 = f2ord(q.y); x2 = f2ord(q.z); y2 = f2ord(q.w);
         amin = amax = f2ord((q.z - q.x) * (q.w - q.y));
         c0 = c1 = cls;
@@ -566,7 +564,7 @@ __device__ __forceinline__ void cand_process(const GArgs& a, EdgeWarp& w, const 
     const size_t off = (size_t)b * a.cap;
     const float4* __restrict__ sb = a.sboxes + (size_t)b * a.scap;
     const u32* __restrict__ skey = a.skey + off;
-    const u32* __restrict__ sidx = a.sidx + off;
+    const u32* __restrict__ sidx = a.pos + off;   // position -> original index (graph_spatial_kernel)
     const u32* __restrict__ scls = a.scls + off;
     uint2* __restrict__ edges = a.edges + (u64)b * a.edges_per_img;
     const int lane = threadIdx.x & 31;
@@ -703,10 +701,16 @@ __device__ __forceinline__ void edge_chunk(const GArgs& a, EdgeWarp& w, const in
         if (!__any_sync(0xffffffffu, h2_any_ge0(x))) continue;   // NaN (no overlap at all) is not a candidate
         // queue the candidates: (row, first column of the hit) in one ballot; a lane whose two columns both hit
         // (rare) queues the second one in another round
-        const u32 hit = ro < (u32)(kTile * sizeof(Rec16)) ? h2_ge0_bits(x) : 0u;   // padding items never
         const u32 i = ro / (u32)sizeof(Rec16);
         const u32 qp = sub[co / (u32)(4 * sizeof(Rec16))] * kSub + 2 * j;
+        // every unordered pair once, and never a box with itself (each box passes the filter against itself: that
+        // alone was 1.5 of the 3.2 candidates per edge); padding items never
+        const u32 rp = (u32)I * kTile + i;
+        u32 hit = ro < (u32)(kTile * sizeof(Rec16)) ? h2_ge0_bits(x) : 0u;
+        if (qp <= rp) hit &= 2u;
+        if (qp + 1u <= rp) hit = 0u;
         const unsigned m0 = __ballot_sync(0xffffffffu, hit != 0u);
+        if (m0 == 0u) continue;   // only self / mirrored pairs of a diagonal tile
         if (hit) w.cand[n_cand + __popc(m0 & lt_mask)] = (i << 24) | (qp + (hit == 2u ? 1u : 0u));
         n_cand += __popc(m0);
         const unsigned m1 = __ballot_sync(0xffffffffu, hit == 3u);
@@ -1188,7 +1192,7 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
 
 // ---- host side -------------------------------------------------------------------------------
 struct GLayout {
-    size_t k[2], order, rinv, pos, sboxes, skey, sidx, scls, tstat, sstat, info, iflags, ticket, edges, total;
+    size_t k[2], order, rinv, pos, sboxes, skey, scls, tstat, sstat, info, iflags, ticket, edges, total;
 };
 
 static inline size_t g_align(size_t x) { return (x + 255) / 256 * 256; }
@@ -1205,7 +1209,6 @@ static GLayout graph_layout(int B, int cap) {
     L.pos = o; o = g_align(o + n * 4);
     L.sboxes = o; o = g_align(o + (size_t)B * (((size_t)cap + kSub - 1) / kSub * kSub) * 16);
     L.skey = o; o = g_align(o + n * 4);
-    L.sidx = o; o = g_align(o + n * 4);
     L.scls = o; o = g_align(o + n * 4);
     L.tstat = o; o = g_align(o + (size_t)B * tcap * 32);
     L.sstat = o; o = g_align(o + (size_t)B * tcap * kSubs * 32);
@@ -1275,7 +1278,7 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     a.k0 = (u32*)(w + L.k[0]); a.v0 = (u32*)(w + L.k[1]);
     a.n_score_chunks = (cap + kScoreChunk - 1) / kScoreChunk;
     a.order = (u32*)(w + L.order); a.rinv = (u32*)(w + L.rinv); a.pos = (u32*)(w + L.pos);
-    a.sboxes = (float4*)(w + L.sboxes); a.skey = (u32*)(w + L.skey); a.sidx = (u32*)(w + L.sidx); a.scls = (u32*)(w + L.scls);
+    a.sboxes = (float4*)(w + L.sboxes); a.skey = (u32*)(w + L.skey); a.scls = (u32*)(w + L.scls);
     a.tstat = (float4*)(w + L.tstat);
     a.sstat = (float4*)(w + L.sstat);
     a.info = (GImg*)(w + L.info);
