@@ -83,7 +83,7 @@ struct GArgs {
     u32* scls;                         // (B,cap) position -> class id (per-class mode)
     int* iflags;                       // (B) per-image flags ORed by the chunks of the spatial kernel (zeroed per call)
     int n_chunks;                      // spatial chunks per image
-    u32 resolve_smem_edges;            // edges per image the resolve kernel can hold in shared memory
+    u32 resolve_smem_words;            // 32-bit words of shared memory the resolve kernel has for the edge list
     float4* tstat;                     // (B,tcap,2) tile bbox | {amin, amax, cmin, cmax}
     float4* sstat;                     // (B,tcap,kSubs,2) sub-tile bbox | {amin, amax, -, -}
     GImg* info;
@@ -1096,12 +1096,13 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
     uint2* gedges = a.edges + (u64)b * a.edges_per_img;
     const u32 E = info.n_edges;
     // The edge kernel recorded ORIGINAL indices (it does not wait for the score sort): to score ranks, once — and,
-    // when the list fits, into shared memory, so that the rounds below never touch global memory.
-    uint2* sedges = reinterpret_cast<uint2*>(s_bits + 4 * nw_cap);   // 16-byte aligned: 4 * nw_cap words
-    const uint2* edges = E <= a.resolve_smem_edges ? sedges : gedges;
+    // when the list fits, into shared memory (two 16-bit ranks per word when M <= 65536: 37 K edges per image at
+    // 640^2), so that the rounds below never touch global memory.
+    u32* sedges = s_bits + 4 * nw_cap;
+    const bool pack16 = M <= 65536 && E <= a.resolve_smem_words;
+    const bool in_smem = pack16 || 2u * E <= a.resolve_smem_words;
     {
         const u32* __restrict__ rinv = a.rinv + (size_t)b * a.cap;
-        uint2* dst = E <= a.resolve_smem_edges ? sedges : gedges;
         // four edges per thread and step: the loads of a step are independent (12 in flight per thread)
         for (u32 e0 = tid; e0 < E; e0 += 4 * kResolveThreads) {
             uint2 sd[4];
@@ -1116,21 +1117,46 @@ __global__ void __launch_bounds__(kResolveThreads) graph_resolve_kernel(const GA
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const u32 e = e0 + k * kResolveThreads;
-                if (e < E) dst[e] = make_uint2(rx[k], ry[k]);
+                if (e < E) {
+                    if (pack16) sedges[e] = (rx[k] << 16) | ry[k];
+                    else if (in_smem) reinterpret_cast<uint2*>(sedges)[e] = make_uint2(rx[k], ry[k]);
+                    else gedges[e] = make_uint2(rx[k], ry[k]);
+                }
             }
         }
     }
     __syncthreads();
+    // Every thread owns a contiguous segment of the list and compacts it in place: an edge whose destination has
+    // been decided, or whose source has been suppressed, can never matter again (odd segment length: the strided
+    // shared-memory accesses of a warp fall into 32 different banks).
+    const u32 per = ((E + kResolveThreads - 1) / kResolveThreads) | 1u;
+    const u32 my_beg = min((u32)tid * per, E);
+    u32 my_n = min(per, E - my_beg);
+    auto load_edge = [&](u32 e) -> uint2 {
+        if (pack16) { const u32 v = sedges[e]; return make_uint2(v >> 16, v & 0xffffu); }
+        return in_smem ? reinterpret_cast<const uint2*>(sedges)[e] : gedges[e];
+    };
+    auto store_edge = [&](u32 e, uint2 v) {
+        if (pack16) sedges[e] = (v.x << 16) | v.y;
+        else if (in_smem) reinterpret_cast<uint2*>(sedges)[e] = v;
+        else gedges[e] = v;
+    };
     for (;;) {
-        for (u32 e = tid; e < E; e += kResolveThreads) {
-            const uint2 sd = edges[e];  // x = higher-scored (lower rank), y = lower-scored
+        u32 live = 0;
+        for (u32 k = 0; k < my_n; ++k) {
+            const uint2 sd = load_edge(my_beg + k);  // x = higher-scored (lower rank), y = lower-scored
             const u32 dw = sd.y >> 5, dbit = 1u << (sd.y & 31);
             if (U[dw] & dbit) {
                 const u32 sw = sd.x >> 5, sbit = 1u << (sd.x & 31);
-                if (K[sw] & sbit) atomicOr(&fK[dw], dbit);
-                else if (U[sw] & sbit) atomicOr(&fU[dw], dbit);
+                if (K[sw] & sbit) atomicOr(&fK[dw], dbit);           // destination suppressed this round: edge done
+                else if (U[sw] & sbit) {
+                    atomicOr(&fU[dw], dbit);
+                    if (live != k) store_edge(my_beg + live, sd);
+                    ++live;
+                }
             }
         }
+        my_n = live;
         __syncthreads();
         int left = 0;
         for (int w = tid; w < nw; w += kResolveThreads) {
@@ -1326,8 +1352,8 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     static_assert(kResolveThreads == 2 * kGreedyT, "greedy_resolve splits the CTA in two halves");
     const size_t bits_bytes = ((size_t)((cap + 31) / 32) * 4 + 2) * 4;
     YB_CHECK_ARG(bits_bytes <= 150 * 1024, "nms(graph): cap too large for the resolve kernel");
-    size_t dyn = 160 * 1024;                      // bitmaps + as many edges as fit (20 K per image at 640^2)
-    a.resolve_smem_edges = (u32)((dyn - bits_bytes) / 8);
+    size_t dyn = 160 * 1024;                      // bitmaps + as many edges as fit
+    a.resolve_smem_words = (u32)((dyn - bits_bytes) / 4);
     if (dyn < sizeof(GreedySmem)) dyn = sizeof(GreedySmem);
     YB_CUDA(cudaFuncSetAttribute(graph_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     YB_LAUNCH("graph_resolve_kernel", st, graph_resolve_kernel<<<B, kResolveThreads, dyn, st>>>(a));
