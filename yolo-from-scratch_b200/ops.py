@@ -641,7 +641,7 @@ def filter_candidates(predictions, anchors_list, img_size, num_classes=1, conf_t
         boxes = torch.empty(B, cap, 4, dtype=torch.float32, device=dev)
         scores = torch.empty(B, cap, dtype=torch.float32, device=dev)
         classes = torch.empty(B, cap, dtype=torch.int64, device=dev)
-        counts = torch.zeros(B, dtype=torch.int32, device=dev)
+        counts = (torch.empty if B > 0 else torch.zeros)(B, dtype=torch.int32, device=dev)   # every image's count is written by the kernel
         lb = None
         if letterbox is not None:
             lb = torch.as_tensor(letterbox, dtype=torch.float32).reshape(B, 3).to(dev).contiguous()
@@ -667,9 +667,10 @@ def batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_
     B, cap = boxes.shape[0], boxes.shape[1]
     L = _lib.lib()
     keep = torch.empty(B, cap, dtype=torch.int64, device=dev)
-    n_keep = torch.zeros(B, dtype=torch.int32, device=dev)
     if B == 0 or cap == 0:
-        return keep, n_keep
+        z = torch.zeros(B, dtype=torch.int32, device=dev)
+        return (keep, z, None) if return_workspace else (keep, z)
+    n_keep = torch.empty(B, dtype=torch.int32, device=dev)   # written for every image (no fill kernel on the critical path)
     need = (L.yb_nms_graph_workspace_bytes(B, cap, GRAPH_EDGES_PER_BOX) if algo == NMS_GRAPH
             else L.yb_nms_workspace_bytes(B, cap))
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -780,7 +781,7 @@ def pack_detections(det):
     B, cap = boxes.shape[0], boxes.shape[1]
     with torch.cuda.device(boxes.device):
         rows = torch.empty(B * cap, 6, dtype=torch.float32, device=boxes.device)
-        offsets = torch.zeros(B + 1, dtype=torch.int32, device=boxes.device)
+        offsets = (torch.empty if B > 0 and cap > 0 else torch.zeros)(B + 1, dtype=torch.int32, device=boxes.device)
         _lib.check(_lib.lib().yb_pack_detections(boxes.data_ptr(), det["scores"].data_ptr(), det["classes"].data_ptr(),
                                                  keep.data_ptr(), det["n_keep"].data_ptr(), B, cap, rows.data_ptr(),
                                                  offsets.data_ptr(), _stream()), "yb_pack_detections")
