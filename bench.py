@@ -696,7 +696,7 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
 
     # ---- a-1: decode_predictions forward / backward on the same heads (2T / 3T bytes) ---------------
     decode = None
-    if full and layout == ops.LAYOUT_BHWAC:
+    if layout == ops.LAYOUT_BHWAC and (full or rank == 0):
         decode = time_decode(lib, dev_sets, anchors, img, nc, n_sets, args.steps)
 
     # ---- e2e through the public API with host buffers ---------------------------------------------

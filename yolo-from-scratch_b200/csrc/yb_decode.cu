@@ -157,6 +157,42 @@ __global__ void __launch_bounds__(256) decode_rows_kernel(const DecodeArgs a) {
     }
 }
 
+// Long rows (nc >= 4, e.g. 85 floats): in the flat walk a quarter of the lanes of every warp holds one of a row's
+// four box channels, so every warp ran the full sigmoid path (300 instructions per float4, ncu: 247 M warp
+// instructions for the 418 MB P3 head, 0.48 of the copy peak).  Here a CTA owns 64 consecutive rows (a 16-byte
+// aligned span for any row length): phase 1 is a pure float4 copy of the span, phase 2 — after a barrier — lets one
+// thread per row overwrite the four box channels with the decoded values (the sectors are still in L2).
+template <bool BWD>
+__global__ void __launch_bounds__(256) decode_long_kernel(const DecodeArgs a) {
+    constexpr uint32_t RPC = 64;   // rows per chunk (multiple of 4: chunk starts are 16-byte aligned)
+    const uint32_t n_rows = a.n_elem / a.row;
+    const uint32_t n_chunks = (n_rows + RPC - 1) / RPC;
+    for (uint32_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const uint32_t r0 = ch * RPC, nr = min(RPC, n_rows - r0);
+        const size_t e0 = (size_t)r0 * a.row;
+        const uint32_t nfl = nr * a.row, nv = nfl / 4u;
+        const float4* __restrict__ src4 = reinterpret_cast<const float4*>((BWD ? a.grad_out : a.pred) + e0);
+        float4* __restrict__ dst4 = reinterpret_cast<float4*>(a.out + e0);
+        for (uint32_t v0 = threadIdx.x; v0 < nv; v0 += 6 * 256) {   // six independent 16-byte loads in flight per thread
+            float4 t[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) if (v0 + k * 256 < nv) t[k] = __ldcs(src4 + v0 + k * 256);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) if (v0 + k * 256 < nv) __stcg(dst4 + v0 + k * 256, t[k]);
+        }
+        for (uint32_t e = nv * 4u + threadIdx.x; e < nfl; e += 256) a.out[e0 + e] = (BWD ? a.grad_out : a.pred)[e0 + e];
+        __syncthreads();
+        if (threadIdx.x < nr) {
+            const uint32_t r = r0 + threadIdx.x;
+            const size_t eb = (size_t)r * a.row;
+#pragma unroll
+            for (uint32_t c = 0; c < 4; ++c)
+                a.out[eb + c] = decode_elem<BWD>(a, r, c, a.pred[eb + c], BWD ? a.grad_out[eb + c] : 0.f);
+        }
+        __syncthreads();
+    }
+}
+
 template <int ROW>
 static void decode_rows_launch(bool bwd, const DecodeArgs& a, int blocks, cudaStream_t st) {
     if (bwd) decode_rows_kernel<ROW, true><<<blocks, 256, 0, st>>>(a);
@@ -198,6 +234,13 @@ static int decode_launch(bool bwd, const float* pred, const float* anchors, cons
             case 7: YB_LAUNCH(name, st, decode_rows_launch<7>(bwd, a, blocks, st)); break;
             default: YB_LAUNCH(name, st, decode_rows_launch<8>(bwd, a, blocks, st)); break;
         }
+        return 0;
+    }
+    if (a.row >= 16) {   // long rows: copy + per-row fix-up
+        unsigned long long chunks = (n / a.row + 63) / 64;
+        blocks = (int)(chunks < 1 ? 1 : (chunks < cap ? chunks : cap));
+        if (bwd) YB_LAUNCH("decode_bwd_kernel", st, decode_long_kernel<true><<<blocks, threads, 0, st>>>(a));
+        else     YB_LAUNCH("decode_fwd_kernel", st, decode_long_kernel<false><<<blocks, threads, 0, st>>>(a));
         return 0;
     }
     if (bwd) YB_LAUNCH("decode_bwd_kernel", st, decode_kernel<true><<<blocks, threads, 0, st>>>(a));
