@@ -1001,6 +1001,61 @@ def test_config1_conf_sweep_keep_sets(yb):
             _check_image_against_oracle_and_torchvision(yb, det, heads, b, img, nc, conf, iou)
 
 
+def _fuzz_boxes(rng, n, kind):
+    """Box sets that stress the half-precision filter's frames and rounding: sizes spanning 6 decades inside one
+    image, extreme aspect ratios, sub-pixel boxes next to image-sized ones, duplicates, jittered clusters, huge
+    coordinate offsets, integer grids."""
+    if kind == "decades":
+        c = rng.uniform(0, 1000, (n, 2)); wh = 10.0 ** rng.uniform(-3, 3, (n, 2))
+    elif kind == "aspect":
+        c = rng.uniform(0, 640, (n, 2)); w = 10.0 ** rng.uniform(-1, 2.5, n); ar = 10.0 ** rng.uniform(-2.5, 2.5, n)
+        wh = np.stack([w, w * ar], 1)
+    elif kind == "clusters":
+        k = max(1, n // 40); cc = rng.uniform(0, 800, (k, 2)); ww = 10.0 ** rng.uniform(0, 2.3, (k, 2))
+        idx = rng.integers(0, k, n)
+        c = cc[idx] + rng.normal(0, 0.08, (n, 2)) * ww[idx]; wh = ww[idx] * np.exp(rng.normal(0, 0.12, (n, 2)))
+    elif kind == "offset":
+        c = rng.uniform(0, 300, (n, 2)) + 3.0e5; wh = rng.uniform(1, 120, (n, 2))
+    elif kind == "grid":
+        c = rng.integers(0, 64, (n, 2)).astype(np.float64) * 8.0; wh = rng.integers(1, 6, (n, 2)).astype(np.float64) * 8.0
+    else:  # "tiny": sub-pixel boxes spread over a large image, plus a few big ones
+        c = rng.uniform(0, 2000, (n, 2)); wh = 10.0 ** rng.uniform(-4, -1, (n, 2))
+        big = rng.random(n) < 0.05
+        wh[big] = rng.uniform(100, 900, (int(big.sum()), 2))
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    dup = rng.random(n) < 0.05                      # exact duplicates
+    boxes[dup] = boxes[rng.integers(0, n, int(dup.sum()))]
+    scores = rng.random(n).astype(np.float32)
+    scores[rng.random(n) < 0.1] = scores[0]         # score ties
+    return torch.from_numpy(boxes), torch.from_numpy(scores)
+
+
+@pytest.mark.parametrize("kind", ["decades", "aspect", "clusters", "offset", "grid", "tiny"])
+def test_nms_fuzz_against_torchvision(yb, kind):
+    """The graph algorithm's half-precision filter may only ADD work, never lose an edge: keep sets equal
+    torchvision's CUDA kernels bit for bit on adversarial box distributions, thresholds from 0.03 to 0.9, with and
+    without classes, batched with ragged counts."""
+    import torchvision
+    rng = np.random.default_rng({"decades": 11, "aspect": 12, "clusters": 13, "offset": 14, "grid": 15, "tiny": 16}[kind])
+    for trial, thr in enumerate((0.03, 0.1, 0.3, 0.4, 0.5, 0.7, 0.9)):
+        B = 3
+        ns = [int(rng.integers(1, 9000)) for _ in range(B)]
+        cap = max(ns)
+        boxes = torch.zeros(B, cap, 4); scores = torch.zeros(B, cap); classes = torch.zeros(B, cap, dtype=torch.int64)
+        sets = []
+        for b, n in enumerate(ns):
+            bx, sc = _fuzz_boxes(rng, n, kind)
+            cl = torch.from_numpy(rng.integers(0, 1 if trial % 2 else 12, n))
+            boxes[b, :n], scores[b, :n], classes[b, :n] = bx, sc, cl
+            sets.append((bx, sc, cl))
+        counts = torch.tensor(ns, dtype=torch.int32)
+        keep, n_keep = yb.batched_nms_padded(boxes.cuda(), scores.cuda(), classes.cuda(), counts.cuda(), thr)
+        for b, (bx, sc, cl) in enumerate(sets):
+            want = torchvision.ops.batched_nms(bx.cuda(), sc.cuda(), cl.cuda(), thr)
+            got = keep[b, :int(n_keep[b])]
+            assert torch.equal(got, want), (kind, thr, b, int(n_keep[b]), int(want.numel()))
+
+
 def test_launch_counter_and_library(yb):
     lib = yb._lib.lib()
     before = lib.yb_launch_count()

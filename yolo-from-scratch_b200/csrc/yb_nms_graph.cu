@@ -277,12 +277,12 @@ __global__ void __launch_bounds__(kSpThreads) graph_spatial_kernel(const GArgs a
         if (tid == 0 && chunk == 0) {
             GImg z = {0, G_PLAIN, 0, 0, 0, 0u, 0.0f, -1.0f, 0ull, 0ull};
             *info = z;
+            if (a.n_chunks == 1) a.iflags[b] = 0;
         }
         return;
     }
     const float4* boxes = a.boxes + off + c0;
     const int64_t* classes = a.classes ? a.classes + off + c0 : nullptr;
-    const float* scores = a.scores + off + c0;
     const int ccap = (min(a.cap, kChunk) + 7) & ~7;
     u32* hist = s_dyn;
     unsigned short* keys = reinterpret_cast<unsigned short*>(s_dyn + NB);
@@ -335,7 +335,10 @@ __global__ void __launch_bounds__(kSpThreads) graph_spatial_kernel(const GArgs a
     // 2: class ids beyond the key; 4: boxes or threshold the half-precision filter cannot serve (NaN/Inf, inverted,
     // |coordinate| > 1e17, thr outside [0.03, 1e30]).  Both are decided by the resolve kernel's greedy pass.
     const int flags = ((bad & 2) ? 2 : 0) | (exact ? 4 : 0);
-    if (flags && tid == 0) atomicOr(a.iflags + b, flags);
+    if (tid == 0) {
+        if (a.n_chunks == 1) a.iflags[b] = flags;          // the only chunk: a plain store, no memset node before the launch
+        else if (flags) atomicOr(a.iflags + b, flags);     // several chunks OR into a word the host zeroed
+    }
 
     // ---- key layout of this chunk ----
     KeyBits kb;
@@ -1336,7 +1339,7 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     if (fj) YB_CUDA(cudaEventRecord(fj->join[slot], fj->side));
 
     // ---- main branch: spatial order + gather, edge discovery ----
-    YB_CUDA(cudaMemsetAsync(a.iflags, 0, (size_t)B * sizeof(int), st));
+    if (a.n_chunks > 1) YB_CUDA(cudaMemsetAsync(a.iflags, 0, (size_t)B * sizeof(int), st));
     {
         const size_t smem = spatial_smem_bytes(cap < kChunk ? cap : kChunk);
         YB_CUDA(cudaFuncSetAttribute(graph_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
