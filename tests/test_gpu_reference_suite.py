@@ -187,3 +187,73 @@ def test_rebound_predict_reproduces_the_reference_goldens(tmp_path, golden, name
     many = train.predict_batch(_PresetHeads([torch.cat([h, h]) for h in heads], int(img), model.anchors), [path, path], dev,
                                num_classes=int(nc), conf_threshold=float(conf), iou_threshold=float(iou))
     assert len(many) == 2 and many[0] == dets and many[1] == dets
+
+
+@pytest.mark.parametrize("nc", [1, 80])
+def test_channels_last_model_hands_over_heads_without_the_permute_copy(nc):
+    """f-2 inside the drop-in flow: with install(..., channels_last=True) the UNCHANGED `train.YOLO` runs in NHWC,
+    the three tensors `forward` returns (train.py:608-609) alias the head convs' outputs (no view/permute/contiguous
+    copy), and loss + gradients through the swap equal the default NCHW model's and the oracle's on the same heads."""
+    _need_ref()
+    sys.path.insert(0, REF)
+    from yolo_from_scratch_b200.install import enable_import_hook, channels_last_heads
+    enable_import_hook()
+    import train
+    from oracle import ref_path as R
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    plain = train.YOLO(num_classes=nc, img_size=320).to(dev).train()
+    nhwc = train.YOLO(num_classes=nc, img_size=320).to(dev).train()
+    nhwc.load_state_dict(plain.state_dict())
+    channels_last_heads(nhwc)
+    assert nhwc.head_p3.weight.is_contiguous(memory_format=torch.channels_last)
+    seen = {}
+    hooks = [h.register_forward_hook(lambda m, i, o, k=k: seen.__setitem__(k, o))
+             for k, h in enumerate((nhwc.head_p3, nhwc.head_p4, nhwc.head_p5))]
+    x = torch.rand(4, 3, 320, 320, device=dev)
+    heads = nhwc(x)
+    for k, h in enumerate(heads):
+        assert h.is_contiguous() and h.shape[-1] == 5 + nc
+        assert h.data_ptr() == seen[k].data_ptr(), "head %d was copied" % k
+    for h in hooks:
+        h.remove()
+    heads_plain = plain(x)
+    for a, b in zip(heads, heads_plain):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-3)
+    rng = np.random.default_rng(5)
+    labels = [np.column_stack([rng.integers(0, nc, 3), rng.uniform(0.2, 0.8, (3, 2)), rng.uniform(0.05, 0.4, (3, 2))]).astype(np.float64)
+              for _ in range(4)]
+    grids = [h.shape[1] for h in heads]
+    tg = [torch.from_numpy(np.stack(t)).to(dev) for t in zip(*[R.assign_targets(l, R.default_anchors(), grids, nc, 320) for l in labels])]
+    out = train.yolo_loss_multiscale(heads, tg, nhwc.anchors, nc)
+    out[0].backward()
+    out_plain = train.yolo_loss_multiscale(heads_plain, tg, plain.anchors, nc)
+    out_plain[0].backward()
+    want = R.multiscale_loss([h.detach().cpu() for h in heads], [t.cpu() for t in tg], R.default_anchors(), nc)
+    for got, w in zip(out, want[:4]):
+        assert abs(float(got) - float(w)) <= 2e-5 * max(1.0, abs(float(w)))
+    for got, w in zip(out, out_plain):
+        assert abs(float(got) - float(w)) <= 2e-3 * max(1.0, abs(float(w)))
+    ga, gb = nhwc.head_p3.weight.grad, plain.head_p3.weight.grad
+    assert ga is not None and torch.isfinite(ga).all()
+    assert float((ga - gb).abs().max()) <= 2e-2 * float(gb.abs().max()) + 1e-6
+
+
+def test_reference_cli_trains_with_channels_last_heads(tmp_path):
+    """The unchanged CLI (train.py:1520-1522) with YOLO_B200_CHANNELS_LAST=1: one epoch, finite losses, checkpoint
+    written and readable by the UNPATCHED reference's eval mode (the state dict keeps the reference's shapes)."""
+    _need_ref()
+    cfg, dirs = _make_dataset(tmp_path)
+    train_py = os.path.join(REF, "train.py")
+    env = _env()
+    env["YOLO_B200_CHANNELS_LAST"] = "1"
+    p = subprocess.run([sys.executable, "-m", "yolo_from_scratch_b200.run", train_py, cfg, "--epochs", "1", "--img-size", "320",
+                        "--size", "n"], capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=1500)
+    _log("reference_cli_channels_last.log", p.stdout[-6000:] + "\n--- stderr ---\n" + p.stderr[-3000:])
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "Epoch 1:" in p.stdout and "Training complete" in p.stdout and "nan" not in p.stdout.lower()
+    ckpts = sorted(f for f in os.listdir(tmp_path) if f.startswith("yolo_") and f.endswith(".pt"))
+    assert len(ckpts) == 1
+    q = subprocess.run([sys.executable, train_py, cfg, str(tmp_path / ckpts[0]), "--size", "n"], capture_output=True, text=True,
+                       env=_env(), cwd=str(tmp_path), timeout=1500)
+    assert q.returncode == 0 and "F1 Score:" in q.stdout, q.stdout[-2000:] + q.stderr[-2000:]

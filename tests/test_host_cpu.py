@@ -196,6 +196,48 @@ def test_install_on_live_reference(yb, reference_module):
         inst.uninstall(ref)
 
 
+def test_channels_last_option_removes_the_head_permute_copy(yb):
+    """f-2 in the drop-in flow: install(..., channels_last=True) makes every model built afterwards run NHWC, so the
+    reference's view/permute/contiguous of a head conv's output (train.py:608-609) returns an alias of the conv's
+    output; uninstall restores the constructor.  Host logic only (a stand-in model with the reference's head code)."""
+    import torch
+    from yolo_from_scratch_b200 import install as inst
+    m, _ = fake_train_module()
+
+    class YOLO(torch.nn.Module):
+        def __init__(self, nc=2):
+            super().__init__()
+            self.nc = nc
+            self.body = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.BatchNorm2d(8), torch.nn.SiLU())
+            self.head = torch.nn.Conv2d(8, 3 * (5 + nc), 1)
+
+        def forward(self, x):
+            self.raw = self.head(self.body(x))
+            b, _, h, w = self.raw.shape
+            return self.raw.view(b, 3, 5 + self.nc, h, w).permute(0, 3, 4, 1, 2).contiguous()
+    m.YOLO = YOLO
+    orig_init = YOLO.__init__
+    x = torch.randn(2, 3, 16, 16)
+    torch.manual_seed(0)
+    plain = YOLO()
+    out_plain = plain(x)
+    assert out_plain.data_ptr() != plain.raw.data_ptr()          # the reference pays a copy here
+    inst.install(m, channels_last=True)
+    try:
+        model = m.YOLO()
+        model.load_state_dict(plain.state_dict())
+        out = model(x)
+        assert out.is_contiguous() and out.shape == (2, 16, 16, 3, 7)
+        assert out.data_ptr() == model.raw.data_ptr()             # alias of the conv output: no copy
+        assert torch.allclose(out, out_plain, atol=1e-5)
+        out.sum().backward()
+        assert model.head.weight.grad is not None
+        assert inst.channels_last_heads(model) is model           # idempotent
+    finally:
+        inst.uninstall(m)
+    assert YOLO.__init__ is orig_init
+
+
 def test_eval_epoch_is_rebound_and_restored(yb):
     from yolo_from_scratch_b200 import install as inst, ops
     m, _ = fake_train_module()

@@ -92,6 +92,39 @@ def _make_predict(train_module):
     return predict, predict_batch
 
 
+def channels_last_heads(model):
+    """SURVEY 8f-2 for the UNCHANGED model: run the network in NHWC (`torch.channels_last`).  The head convs
+    then write (B, H, W, A*(5+nc)) in memory, on which train.py:608-609's view/permute is a pure stride change and
+    `.contiguous()` returns its argument: the three heads reach the loss / decode kernels in the reference's
+    (B,H,W,A,5+nc) layout WITHOUT the copy pass (the returned tensors alias the conv outputs), and the
+    gradient flows back to the conv the same way.  Idempotent; returns the model."""
+    import torch
+    if getattr(model, "__yolo_b200_channels_last__", False):
+        return model
+    model.to(memory_format=torch.channels_last)
+
+    def _nhwc_input(_module, args):
+        x = args[0]
+        if x.dim() == 4 and not x.is_contiguous(memory_format=torch.channels_last):
+            return (x.contiguous(memory_format=torch.channels_last),) + tuple(args[1:])
+        return None
+    model.register_forward_pre_hook(_nhwc_input)
+    model.__yolo_b200_channels_last__ = True
+    return model
+
+
+def _wrap_model_init(train_module):
+    cls = train_module.YOLO
+    orig = cls.__init__
+
+    def __init__(self, *args, **kwargs):
+        orig(self, *args, **kwargs)
+        channels_last_heads(self)
+    __init__.__wrapped__ = orig
+    cls.__init__ = __init__
+    return orig
+
+
 def _in_dataloader_worker():
     try:
         import torch.utils.data
@@ -100,8 +133,11 @@ def _in_dataloader_worker():
         return False
 
 
-def install(train_module, patch_torchvision=False, patch_dataset=True, patch_eval=True, patch_predict=True):
+def install(train_module, patch_torchvision=False, patch_dataset=True, patch_eval=True, patch_predict=True,
+            channels_last=None):
     """Rebind the hot-path names of an imported reference `train` module.  Idempotent.
+    channels_last (default: environment YOLO_B200_CHANNELS_LAST=1) makes every `train.YOLO` built afterwards
+    run in NHWC, so that the head layout conversion of train.py:608-609 costs nothing (channels_last_heads).
     patch_eval also swaps `eval_epoch` (SURVEY 8f-1: its per-anchor python loop becomes one kernel);
     patch_predict swaps `predict` and adds `predict_batch`; patch_torchvision additionally
     rebinds torchvision.ops.batched_nms process-wide (off by default: predict no longer needs it)."""
@@ -123,6 +159,11 @@ def install(train_module, patch_torchvision=False, patch_dataset=True, patch_eva
         saved["YOLODataset.compute_anchor_iou"] = cls.compute_anchor_iou
         cls.__getitem__ = _make_getitem(train_module)
         cls.compute_anchor_iou = lambda self, box_wh, anchors: ops.compute_anchor_iou(box_wh, anchors)
+    if channels_last is None:
+        import os
+        channels_last = os.environ.get("YOLO_B200_CHANNELS_LAST", "0") == "1"
+    if channels_last and hasattr(train_module, "YOLO"):
+        saved["YOLO.__init__"] = _wrap_model_init(train_module)
     if patch_torchvision:
         import torchvision
         import torchvision.ops.boxes as tvb
@@ -149,6 +190,8 @@ def uninstall(train_module):
     if "YOLODataset.__getitem__" in saved:
         train_module.YOLODataset.__getitem__ = saved["YOLODataset.__getitem__"]
         train_module.YOLODataset.compute_anchor_iou = saved["YOLODataset.compute_anchor_iou"]
+    if "YOLO.__init__" in saved:
+        train_module.YOLO.__init__ = saved["YOLO.__init__"]
     if "torchvision.ops.batched_nms" in saved:
         import torchvision
         import torchvision.ops.boxes as tvb
