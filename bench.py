@@ -879,8 +879,21 @@ def time_decode(lib, dev_sets, anchors, img, nc, n_sets, steps):
             B, H, W, A, row = h.shape
             lib.yb_decode_bwd(h.data_ptr(), anchors[s].data_ptr(), dev_sets[(i + 1) % n_sets][0][s].data_ptr(),
                               outs[i % 2][s].data_ptr(), B, H, W, A, row - 5, float(img), st)
+    T3 = tensor_bytes(dev_sets[0][0][:1])
+
+    def fwd_p3(i):   # the reference's call is per scale (train.py:796): the P3 head alone is the launch that carries the bytes
+        h = dev_sets[i % n_sets][0][0]
+        B, H, W, A, row = h.shape
+        lib.yb_decode_fwd(h.data_ptr(), anchors[0].data_ptr(), outs[i % 2][0].data_ptr(), B, H, W, A, row - 5, float(img), st)
+
+    def bwd_p3(i):
+        h = dev_sets[i % n_sets][0][0]
+        B, H, W, A, row = h.shape
+        lib.yb_decode_bwd(h.data_ptr(), anchors[0].data_ptr(), dev_sets[(i + 1) % n_sets][0][0].data_ptr(),
+                          outs[i % 2][0].data_ptr(), B, H, W, A, row - 5, float(img), st)
     res = {}
-    for name, fn, nbytes in (("decode_fwd(3 scales)", fwd, 2 * T), ("decode_bwd(3 scales)", bwd, 3 * T)):
+    for name, fn, nbytes in (("decode_fwd(3 scales)", fwd, 2 * T), ("decode_bwd(3 scales)", bwd, 3 * T),
+                             ("decode_fwd(P3)", fwd_p3, 2 * T3), ("decode_bwd(P3)", bwd_p3, 3 * T3)):
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()

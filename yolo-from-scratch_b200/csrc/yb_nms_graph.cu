@@ -155,14 +155,13 @@ struct KeyBits {
     u32 bmin;
     float cmin, qs;
 };
-__device__ __forceinline__ u32 spatial_key(const float4 q, const int64_t* classes, int i, const KeyBits& kb,
-                                           const unsigned short* lut) {
+__device__ __forceinline__ u32 spatial_key(const float4 q, const u32 cls, const KeyBits& kb, const unsigned short* lut) {
     const u32 bucket = area_bucket(q);
     const float fx = fminf(fmaxf(((q.x + q.z) * 0.5f - kb.cmin) * kb.qs, 0.0f), 255.0f);
     const float fy = fminf(fmaxf(((q.y + q.w) * 0.5f - kb.cmin) * kb.qs, 0.0f), 255.0f);
     u32 curve = hilbert8(lut, (u32)fx, (u32)fy);
     if (bucket & 1u) curve ^= 0xffffu;
-    const u32 c = classes ? ((u32)classes[i] & 0x1ffu) : 0u;
+    const u32 c = cls & 0x1ffu;
     return ((c << kb.cls_shift) | (((bucket - kb.bmin) >> kb.bkt_drop) << kb.bkt_shift) | (curve >> kb.curve_drop)) &
            ((1u << kKeyBits) - 1u);
 }
@@ -249,6 +248,7 @@ __global__ void __launch_bounds__(256) graph_score_merge_kernel(const GArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kChunk = 26880;        // 840 tiles; u16 indices
 constexpr int kSpThreads = 1024;
+constexpr int kSpBatch = 4;
 
 __host__ __device__ inline size_t spatial_smem_bytes(int ccap) {
     return ((size_t)1 << kKeyBits) * sizeof(u32) + 2 * (((size_t)ccap + 7) / 8 * 8) * sizeof(unsigned short) +
@@ -267,6 +267,13 @@ __global__ void __launch_bounds__(kSpThreads) graph_spatial_kernel(const GArgs a
 
     const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t off = (size_t)b * a.cap;
+    {   // lookup table of the curve, zeroed histogram
+        const int ccap0 = (min(a.cap, kChunk) + 7) & ~7;
+        unsigned short* lut0 = reinterpret_cast<unsigned short*>(s_dyn + NB) + 2 * ccap0;
+        lut0[tid] = hilbert_lut_entry(tid >> 8, (u32)(tid >> 4) & 15u, (u32)tid & 15u);
+#pragma unroll
+        for (int k = 0; k < NB / NT; ++k) s_dyn[k * NT + tid] = 0u;
+    }
     int M = a.counts ? a.counts[b] : a.cap;
     M = M < 0 ? 0 : (M > a.cap ? a.cap : M);
     GImg* info = a.info + b;
@@ -289,30 +296,43 @@ __global__ void __launch_bounds__(kSpThreads) graph_spatial_kernel(const GArgs a
     unsigned short* oidx = keys + ccap;
     unsigned short* lut = oidx + ccap;
 
-    lut[tid] = hilbert_lut_entry(tid >> 8, (u32)(tid >> 4) & 15u, (u32)tid & 15u);
-#pragma unroll
-    for (int k = 0; k < NB / NT; ++k) hist[k * NT + tid] = 0u;
 
     // ---- reductions (torchvision's boxes.max(), validity, centre range, class range, bucket range) ----
     const int mode = !a.classes ? G_PLAIN : ((long long)M * 4 <= a.trick_max_numel ? G_TRICK : G_CLASS);
     float mx = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
     int bad = 0, maxcls = 0, bmin = 127, bmax = 0;
-    for (int i = tid; i < Mc; i += NT) {
-        const float4 q = boxes[i];
-        mx = fmaxf(mx, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
-        const bool nan = (q.x != q.x) || (q.y != q.y) || (q.z != q.z) || (q.w != q.w);
-        const float big = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w)));
-        bad |= (nan ? 4 : 0) | ((nan || !(big <= 1e17f) || !(q.z >= q.x) || !(q.w >= q.y)) ? 1 : 0);
-        const float cx = (q.x + q.z) * 0.5f, cy = (q.y + q.w) * 0.5f;
-        cmin = fminf(cmin, fminf(cx, cy));
-        cmax = fmaxf(cmax, fmaxf(cx, cy));
-        const int bk = (int)area_bucket(q);
-        bmin = min(bmin, bk);
-        bmax = max(bmax, bk);
-        if (classes) {
-            const long long c = classes[i];
-            bad |= (c < 0 || c >= 512) ? 2 : 0;
-            maxcls = max(maxcls, (int)(c & 0x1ff));
+    // kSpBatch independent loads in flight per thread: with one CTA per image the passes over the boxes are
+    // latency-bound (ncu: two loads in flight, 1.4 TB/s from L2)
+    for (int i0 = tid; i0 < Mc; i0 += kSpBatch * NT) {
+        float4 qv[kSpBatch];
+        long long cv[kSpBatch];
+#pragma unroll
+        for (int u = 0; u < kSpBatch; ++u) {
+            const int i = i0 + u * NT;
+            if (i < Mc) {
+                qv[u] = __ldg(boxes + i);
+                cv[u] = classes ? __ldg(classes + i) : 0ll;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kSpBatch; ++u) {
+            if (i0 + u * NT >= Mc) break;
+            const float4 q = qv[u];
+            mx = fmaxf(mx, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+            const bool nan = (q.x != q.x) || (q.y != q.y) || (q.z != q.z) || (q.w != q.w);
+            const float big = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w)));
+            bad |= (nan ? 4 : 0) | ((nan || !(big <= 1e17f) || !(q.z >= q.x) || !(q.w >= q.y)) ? 1 : 0);
+            const float cx = (q.x + q.z) * 0.5f, cy = (q.y + q.w) * 0.5f;
+            cmin = fminf(cmin, fminf(cx, cy));
+            cmax = fmaxf(cmax, fmaxf(cx, cy));
+            const int bk = (int)area_bucket(q);
+            bmin = min(bmin, bk);
+            bmax = max(bmax, bk);
+            if (classes) {
+                const long long c = cv[u];
+                bad |= (c < 0 || c >= 512) ? 2 : 0;
+                maxcls = max(maxcls, (int)(c & 0x1ff));
+            }
         }
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
@@ -358,10 +378,25 @@ __global__ void __launch_bounds__(kSpThreads) graph_spatial_kernel(const GArgs a
     // (the block reductions above ended with a barrier: lut and the zeroed histogram are visible)
 
     // ---- counting sort by key: histogram, exclusive scan, scatter ----
-    for (int i = tid; i < Mc; i += NT) {
-        const u32 k = spatial_key(boxes[i], classes, i, kb, lut);
-        keys[i] = (unsigned short)k;
-        atomicAdd(&hist[k], 1u);
+    for (int i0 = tid; i0 < Mc; i0 += kSpBatch * NT) {
+        float4 qv[kSpBatch];
+        u32 cv[kSpBatch];
+#pragma unroll
+        for (int u = 0; u < kSpBatch; ++u) {
+            const int i = i0 + u * NT;
+            if (i < Mc) {
+                qv[u] = __ldg(boxes + i);
+                cv[u] = classes ? (u32)__ldg(classes + i) : 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kSpBatch; ++u) {
+            const int i = i0 + u * NT;
+            if (i >= Mc) break;
+            const u32 k = spatial_key(qv[u], cv[u], kb, lut);
+            keys[i] = (unsigned short)k;
+            atomicAdd(&hist[k], 1u);
+        }
     }
     __syncthreads();
     {
@@ -383,7 +418,19 @@ __global__ void __launch_bounds__(kSpThreads) graph_spatial_kernel(const GArgs a
         for (int k = 0; k < PER; ++k) { hist[tid * PER + k] = base; base += v[k]; }
     }
     __syncthreads();
-    for (int i = tid; i < Mc; i += NT) oidx[atomicAdd(&hist[keys[i]], 1u)] = (unsigned short)i;
+    for (int i0 = tid; i0 < Mc; i0 += kSpBatch * NT) {   // the returning atomics of a batch are in flight together
+        u32 d[kSpBatch];
+#pragma unroll
+        for (int u = 0; u < kSpBatch; ++u) {
+            const int i = i0 + u * NT;
+            if (i < Mc) d[u] = atomicAdd(&hist[keys[i]], 1u);
+        }
+#pragma unroll
+        for (int u = 0; u < kSpBatch; ++u) {
+            const int i = i0 + u * NT;
+            if (i < Mc) oidx[d[u]] = (unsigned short)i;
+        }
+    }
     __syncthreads();
 
     // ---- position -> original index (the gather runs as its own, machine-wide launch) ----
@@ -446,10 +493,18 @@ __global__ void __launch_bounds__(kGatherThreads) graph_gather_kernel(const GArg
         amin = amax = f2ord((q.z - q.x) * (q.w - q.y));
         c0 = c1 = cls;
     }
-    const unsigned sm = 0xffu << (lane & 24);   // this lane's 8-box sub-tile
-    const u32 sx1 = __reduce_min_sync(sm, x1), sy1 = __reduce_min_sync(sm, y1);
-    const u32 sx2 = __reduce_max_sync(sm, x2), sy2 = __reduce_max_sync(sm, y2);
-    const u32 samin = __reduce_min_sync(sm, amin), samax = __reduce_max_sync(sm, amax);
+    // this lane's 8-box sub-tile: three butterfly steps (a REDUX per sub-tile mask runs four times per warp, once per
+    // distinct mask: ncu counted 216 of the kernel's 380 instructions per tile there)
+    u32 sx1 = x1, sy1 = y1, sx2 = x2, sy2 = y2, samin = amin, samax = amax;
+#pragma unroll
+    for (int o = 1; o < kSub; o <<= 1) {
+        sx1 = min(sx1, __shfl_xor_sync(0xffffffffu, sx1, o));
+        sy1 = min(sy1, __shfl_xor_sync(0xffffffffu, sy1, o));
+        sx2 = max(sx2, __shfl_xor_sync(0xffffffffu, sx2, o));
+        sy2 = max(sy2, __shfl_xor_sync(0xffffffffu, sy2, o));
+        samin = min(samin, __shfl_xor_sync(0xffffffffu, samin, o));
+        samax = max(samax, __shfl_xor_sync(0xffffffffu, samax, o));
+    }
     if ((lane & (kSub - 1)) == 0) {
         float4* ss = a.sstat + (((size_t)b * a.tcap + t) * kSubs + (lane / kSub)) * 2;
         // an empty sub-tile (beyond M) keeps +inf/-inf style bounds: it never passes a test (and is never visited)

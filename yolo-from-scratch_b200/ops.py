@@ -759,6 +759,11 @@ def detect_batch(predictions, anchors_list, img_size, num_classes=1, conf_thresh
     """
     boxes, scores, classes, counts = filter_candidates(predictions, anchors_list, img_size, num_classes,
                                                        conf_threshold, letterbox, layout)
+    return nms_candidates(boxes, scores, classes, counts, iou_threshold, trick_max_numel, algo)
+
+
+def nms_candidates(boxes, scores, classes, counts, iou_threshold=0.4, trick_max_numel=TRICK_MAX_NUMEL_CUDA, algo=NMS_GRAPH):
+    """Second half of detect_batch: global NMS (train.py:1232-1233) over the padded candidates of filter_candidates."""
     with torch.cuda.device(boxes.device):
         keep, n_keep, ws = batched_nms_padded(boxes, scores, classes, counts, iou_threshold, trick_max_numel, algo,
                                               return_workspace=True)
@@ -832,7 +837,7 @@ class HotPathGraph:
 
     def __init__(self, batch, img_size, num_classes, anchors_list, conf_threshold=0.5, iou_threshold=0.4, max_gt=50,
                  targets="labels", layout=LAYOUT_BHWAC, num_anchors=3, device=None, adopt_heads=None,
-                 adopt_targets=None, group=None, overlap_loss=True):
+                 adopt_targets=None, group=None, overlap_loss=True, fork_loss="auto"):
         """adopt_heads / adopt_targets: existing device tensors (or a PackedLabels) to use as the static
         inputs instead of allocating new ones.  group: torch.distributed process group of an image-sharded
         job; the all-reduce of the loss partials is then captured inside the graph (NCCL).
@@ -840,6 +845,13 @@ class HotPathGraph:
         are independent readers of the heads; they are captured as two parallel branches of the graph."""
         self.group = group
         self.overlap_loss = bool(overlap_loss)
+        if fork_loss not in ("auto", "start", "after_filter"):
+            raise ValueError("fork_loss must be 'auto', 'start' or 'after_filter'")
+        # Where the loss branch leaves the detection chain.  Short rows (nc <= 3): the loss kernels take about as
+        # long as the two one-CTA-per-image kernels after the filter, so they start there and the filter has the
+        # memory system to itself (measured on B200, nc=1: 295.5 -> 289.2 us per step).  Long rows: the loss is the
+        # longer branch and starts with the filter (nc=80: 572 us against 578).
+        self.fork_loss = ("after_filter" if 5 + int(num_classes) <= 8 else "start") if fork_loss == "auto" else fork_loss
         dev = _device() if device is None else torch.device(device)
         self.device, self.nc, self.img, self.layout = dev, int(num_classes), int(img_size), layout
         row = 5 + self.nc
@@ -889,13 +901,21 @@ class HotPathGraph:
 
     def _step(self):
         cur = torch.cuda.current_stream()
-        if self._branch is not None:      # fork: loss on a second stream, joined before the step ends
+        fork_late = self._branch is not None and self.fork_loss == "after_filter"
+        if self._branch is not None and not fork_late:   # fork: loss on a second stream, joined before the step ends
             self._branch.wait_stream(cur)
             with torch.cuda.stream(self._branch):
                 out4, grads = self._loss()
-        else:
+        elif self._branch is None:
             out4, grads = self._loss()
-        det = detect_batch(self.heads, self.anchors, self.img, self.nc, self.conf, self.iou, layout=self.layout)
+        cand = filter_candidates(self.heads, self.anchors, self.img, self.nc, self.conf, None, self.layout)
+        if fork_late:
+            # the filter and the loss both stream the heads from HBM, while the two kernels after the filter run
+            # one CTA per image: forking here gives the filter the whole memory system and the loss the idle SMs
+            self._branch.wait_stream(cur)
+            with torch.cuda.stream(self._branch):
+                out4, grads = self._loss()
+        det = nms_candidates(*cand, self.iou)
         rows, offsets = pack_detections(det)
         if self._branch is not None:
             cur.wait_stream(self._branch)
