@@ -48,15 +48,6 @@ constexpr int kEdgeThreads = 256;
 #define YB_EDGE_CTAS 4
 #endif
 constexpr int kEdgeCtasPerSM = YB_EDGE_CTAS;
-#ifndef YB_E1
-#define YB_E1 0
-#endif
-#ifndef YB_E2
-#define YB_E2 0
-#endif
-#ifndef YB_E3
-#define YB_E3 0
-#endif
 constexpr int kResolveThreads = 1024;
 
 enum { G_PLAIN = 0, G_TRICK = 1, G_CLASS = 2 };
@@ -799,51 +790,31 @@ __global__ void __launch_bounds__(kEdgeThreads, kEdgeCtasPerSM) graph_edge_kerne
     EdgeWarp& w = s_w[threadIdx.x >> 5];
     const unsigned lt_mask = (1u << lane) - 1u;
     // work items = (row tile, image), all images' tile 0 first, up to the largest image's last tile: with half-full
-    // images (conf 0.5: 394 of 788 tiles) the tickets beyond it were a tail of ~5 empty atomic + load round trips per warp
-#if YB_E2
+    // images (conf 0.5: 394 of 788 tiles) the tickets beyond it are empty atomic + load round trips (1 % of the kernel)
     int max_tiles = 0;
     for (int i = lane; i < a.B; i += 32) max_tiles = max(max_tiles, a.iflags[i] ? 0 : a.info[i].n_tiles);
     max_tiles = __reduce_max_sync(0xffffffffu, max_tiles);
     const u32 total = (u32)max_tiles * (u32)a.B;
-#else
-    const u32 total = (u32)a.tcap * (u32)a.B;
-#endif
 
-#if YB_E1
-    u32 next_ticket = 0;   // taken one work item ahead: the atomic's round trip to L2 overlaps the current item
-    if (lane == 0) next_ticket = atomicAdd(a.ticket, 1u);
-#endif
     for (;;) {
-#if YB_E1
-        const u32 ticket = __shfl_sync(0xffffffffu, next_ticket, 0);
-        if (ticket >= total) break;
-        if (lane == 0) next_ticket = atomicAdd(a.ticket, 1u);
-#else
+        // (taking the ticket one item ahead, to hide the atomic's round trip, measured 6 % SLOWER: a warp then sits on a
+        // reserved item while others run dry at the end)
         u32 ticket = 0;
         if (lane == 0) ticket = atomicAdd(a.ticket, 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket >= total) break;
-#endif
         const int I = (int)(ticket / (u32)a.B), b = (int)(ticket % (u32)a.B);  // all images' tile 0 first
         const float4* sb = a.sboxes + (size_t)b * a.scap;
         const float4* ts = a.tstat + (size_t)b * a.tcap * 2;
         const float4* ss = a.sstat + (size_t)b * a.tcap * kSubs * 2;
         // the item's first loads are issued together with the image record (all in bounds for any I < tcap): one
         // round trip to L2 per work item instead of three dependent ones
-#if YB_E3
         const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
         const int rp = I * kTile + lane;
         const float4 rq = rp < a.scap ? sb[rp] : make_float4(0.f, 0.f, 0.f, 0.f);
         const int flagged = a.iflags[b];
         const GImg info = a.info[b];
         if (I >= info.n_tiles || flagged) continue;
-#else
-        const GImg info = a.info[b];
-        if (I >= info.n_tiles || a.iflags[b]) continue;
-        const float4 ib = ts[I * 2], ia = ts[I * 2 + 1];
-        const int rp = I * kTile + lane;
-        const float4 rq = rp < a.scap ? sb[rp] : make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
         const int M = info.M;
         const float t2 = info.t2;
         const float t3 = a.t3;
