@@ -745,6 +745,31 @@ def run_workload(args, rank, local_rank, world, dev, group, lib, full):
                                         "candidates_per_image": float(det["counts"].double().mean()),
                                         "kept_per_image": float(det["n_keep"].double().mean())}
             del det
+        # SURVEY 8d's "prior" heads: objectness logit 2*randn - 4.6 (a detector's prior: ~4 % of the rows pass conf 0.25)
+        prior_sets = []
+        for k in range(n_sets):
+            hs = [h.clone() for h in dev_sets[k][0]]
+            for h in hs:
+                if layout == 1:   # NCHW: the objectness planes are channels a*row + 4
+                    h[:, 4::5 + nc].mul_(2.0).sub_(4.6)
+                else:
+                    h[..., 4].mul_(2.0).sub_(4.6)
+            prior_sets.append(hs)
+        for i in range(4):
+            ops.detect_batch(prior_sets[i % n_sets], anchors, img, nc, 0.25, args.iou, layout=layout)
+        torch.cuda.synchronize()
+        n_it = max(5, args.steps // 3)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_it + 1)]
+        evs[0].record()
+        for i in range(n_it):
+            det = ops.detect_batch(prior_sets[i % n_sets], anchors, img, nc, 0.25, args.iou, layout=layout)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        ms = float(np.median([evs[i].elapsed_time(evs[i + 1]) for i in range(n_it)]))
+        variants["prior_conf_0.25"] = {"decode_nms_ms": ms, "decode_nms_images_per_s": B / (ms * 1e-3),
+                                       "candidates_per_image": float(det["counts"].double().mean()),
+                                       "kept_per_image": float(det["n_keep"].double().mean())}
+        del det, prior_sets
     barrier()
 
     torch_gpu = None

@@ -1001,6 +1001,24 @@ def test_config1_conf_sweep_keep_sets(yb):
             _check_image_against_oracle_and_torchvision(yb, det, heads, b, img, nc, conf, iou)
 
 
+@pytest.mark.parametrize("nc,conf", [(1, 0.25), (80, 0.25), (80, 0.05)])
+def test_prior_heads_keep_sets(yb, nc, conf):
+    """SURVEY 8d's "prior" variant: objectness logit 2*randn - 4.6 (a detector's prior: a few per cent of the rows
+    pass), i.e. the sparse side of the one-pass filter (most tiles of a group hold no candidate) and small, ragged
+    per-image candidate counts for the NMS; candidates vs the oracle, keep sets vs torchvision's CUDA kernel."""
+    img, B, iou = 640, 6, 0.4
+    g = torch.Generator().manual_seed(77)
+    heads = [torch.randn(B, G, G, 3, 5 + nc, generator=g) for G in (80, 40, 20)]
+    for h in heads:
+        h[..., 4].mul_(2.0).sub_(4.6)
+    heads[1][2, ..., 4] = -30.0          # an image whose P4 head has no candidate at all
+    det = yb.detect_batch([h.cuda() for h in heads], ANCH, img, nc, conf, iou)
+    counts = det["counts"].cpu()
+    assert 0 < int(counts.min()) and int(counts.max()) < 25200 // 4
+    for b in range(B):
+        _check_image_against_oracle_and_torchvision(yb, det, heads, b, img, nc, conf, iou)
+
+
 def _fuzz_boxes(rng, n, kind):
     """Box sets that stress the half-precision filter's frames and rounding: sizes spanning 6 decades inside one
     image, extreme aspect ratios, sub-pixel boxes next to image-sized ones, duplicates, jittered clusters, huge

@@ -10,6 +10,10 @@ dev = torch.device("cuda")
 anchors = ops.default_anchors(dev)
 import itertools
 sets = [[h.to(dev) for h in bench.make_heads(64, 640, 1, 1234 + 1000 * k)] for k in range(1)]
+if os.environ.get("PRIOR") == "1":   # SURVEY 8d's "prior" heads: objectness logit 2*randn - 4.6
+    for hs in sets:
+        for h in hs:
+            h[..., 4].mul_(2.0).sub_(4.6)
 for heads, conf in itertools.product(sets, [float(x) for x in sys.argv[1:]] or [0.5, 0.25, 0.001]):
     for _ in range(3):
         det = ops.detect_batch(heads, anchors, 640, 1, conf, 0.4)
