@@ -847,11 +847,7 @@ class HotPathGraph:
         self.overlap_loss = bool(overlap_loss)
         if fork_loss not in ("auto", "start", "after_filter"):
             raise ValueError("fork_loss must be 'auto', 'start' or 'after_filter'")
-        # Where the loss branch leaves the detection chain.  Short rows (nc <= 3): the loss kernels take about as
-        # long as the two one-CTA-per-image kernels after the filter, so they start there and the filter has the
-        # memory system to itself (measured on B200, nc=1: 295.5 -> 289.2 us per step).  Long rows: the loss is the
-        # longer branch and starts with the filter (nc=80: 572 us against 578).
-        self.fork_loss = ("after_filter" if 5 + int(num_classes) <= 8 else "start") if fork_loss == "auto" else fork_loss
+        self.fork_loss = fork_loss   # "auto" is resolved below, once the kind of targets is known
         dev = _device() if device is None else torch.device(device)
         self.device, self.nc, self.img, self.layout = dev, int(num_classes), int(img_size), layout
         row = 5 + self.nc
@@ -881,6 +877,14 @@ class HotPathGraph:
             else:
                 raise ValueError("targets must be 'labels' or 'dense'")
             self.conf, self.iou = float(conf_threshold), float(iou_threshold)
+            if self.fork_loss == "auto":
+                # Where the loss branch leaves the detection chain.  Short rows (nc <= 3) with dense targets: the loss
+                # kernels take about as long as the two one-CTA-per-image kernels after the filter, so they start there
+                # and the filter has the memory system to itself (B200, nc=1: 295.5 -> 289.2 us per step).  Long rows
+                # or label-list targets (assignment kernels first): the loss is the longer branch, would still be
+                # running when the persistent edge kernel takes every SM, and starts with the filter instead
+                # (nc=80: 572 against 578 us; nc=1 with labels: 291.6 against 294.0 us).
+                self.fork_loss = "after_filter" if (5 + self.nc <= 8 and self.labels is None) else "start"
             self._branch = torch.cuda.Stream(device=dev) if self.overlap_loss else None
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
