@@ -803,7 +803,11 @@ __global__ void __launch_bounds__(kEdgeThreads, kEdgeCtasPerSM) graph_edge_kerne
         if (lane == 0) ticket = atomicAdd(a.ticket, 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket >= total) break;
-        const int I = (int)(ticket / (u32)a.B), b = (int)(ticket % (u32)a.B);  // all images' tile 0 first
+        // Row tiles are handed out from the LAST one down: a row tile only looks at column tiles J >= I, but the order
+        // is by area bucket and the big-box buckets at the end overlap far more sub-tiles (tools/nms_cull_sim.py:
+        // 28 sub-tile pairs per row tile in the first tenth of an image, 60 in the ninth, single tiles up to 160), so
+        // ascending order left the heaviest items for the end of the kernel.
+        const int I = max_tiles - 1 - (int)(ticket / (u32)a.B), b = (int)(ticket % (u32)a.B);
         const float4* sb = a.sboxes + (size_t)b * a.scap;
         const float4* ts = a.tstat + (size_t)b * a.tcap * 2;
         const float4* ss = a.sstat + (size_t)b * a.tcap * kSubs * 2;
