@@ -88,6 +88,7 @@ struct GArgs {
     float4* sstat;                     // (B,tcap,kSubs,2) sub-tile bbox | {amin, amax, -, -}
     GImg* info;
     u32* ticket;
+    u32 ticket_init;                   // warps of the edge kernel: each one's first work item needs no atomic
     uint2* edges;
     u64 edges_per_img;
     int64_t* keep;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kSpThreads) graph_spatial_kernel(const GArgs a
     int M = a.counts ? a.counts[b] : a.cap;
     M = M < 0 ? 0 : (M > a.cap ? a.cap : M);
     GImg* info = a.info + b;
-    if (b == 0 && chunk == 0 && tid == 0) *a.ticket = 0u;
+    if (b == 0 && chunk == 0 && tid == 0) *a.ticket = a.ticket_init;   // the edge kernel's warps own tickets 0..n_warps-1
     const int c0 = chunk * kChunk;
     const int Mc = min(M - c0, kChunk);
     if (Mc <= 0) {
@@ -796,12 +797,17 @@ __global__ void __launch_bounds__(kEdgeThreads, kEdgeCtasPerSM) graph_edge_kerne
     max_tiles = __reduce_max_sync(0xffffffffu, max_tiles);
     const u32 total = (u32)max_tiles * (u32)a.B;
 
+    bool first = true;
     for (;;) {
-        // (taking the ticket one item ahead, to hide the atomic's round trip, measured 6 % SLOWER: a warp then sits on a
-        // reserved item while others run dry at the end)
-        u32 ticket = 0;
-        if (lane == 0) ticket = atomicAdd(a.ticket, 1u);
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        // a warp's first item is its own index (4,736 atomics on one word at kernel start otherwise); after that one
+        // ticket at a time (taking it one item ahead, to hide the atomic's round trip, measured 6 % SLOWER: a warp then
+        // sits on a reserved item while others run dry at the end)
+        u32 ticket = blockIdx.x * (kEdgeThreads / 32) + (threadIdx.x >> 5);
+        if (!first) {
+            if (lane == 0) ticket = atomicAdd(a.ticket, 1u);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        }
+        first = false;
         if (ticket >= total) break;
         // Row tiles are handed out from the LAST one down: a row tile only looks at column tiles J >= I, but the order
         // is by area bucket and the big-box buckets at the end overlap far more sub-tiles (tools/nms_cull_sim.py:
@@ -1382,6 +1388,7 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     a.info = (GImg*)(w + L.info);
     a.iflags = (int*)(w + L.iflags);
     a.ticket = (u32*)(w + L.ticket);
+    a.ticket_init = (u32)(sm_count() * kEdgeCtasPerSM * (kEdgeThreads / 32));
     a.edges = (uint2*)(w + L.edges);
     a.edges_per_img = (ws_bytes - L.edges) / 8 / (size_t)B;
     a.keep = keep; a.n_keep = n_keep;
@@ -1417,6 +1424,7 @@ int graph_nms(const float* boxes, const float* scores, const int64_t* classes, c
     const dim3 ggrid((a.tcap + kGatherThreads / 32 - 1) / (kGatherThreads / 32), B);
     YB_LAUNCH("graph_gather_kernel", st, graph_gather_kernel<<<ggrid, kGatherThreads, 0, st>>>(a));
     const int ctas = sm_count() * kEdgeCtasPerSM;  // resident CTAs per SM (launch bounds)
+    // (a.ticket_init was set before the spatial kernel's launch: it writes the counter)
     YB_LAUNCH("graph_edge_kernel", st, graph_edge_kernel<<<ctas, kEdgeThreads, 0, st>>>(a));
 
     // ---- join, resolve ----
