@@ -21,6 +21,8 @@ for heads, conf in itertools.product(sets, [float(x) for x in sys.argv[1:]] or [
     lib.yb_timing_enable(1)
     for _ in range(5):
         det = ops.detect_batch(heads, anchors, 640, 1, conf, 0.4)
+        if os.environ.get("PACK") == "1":
+            ops.pack_detections(det)
     torch.cuda.synchronize()
     lib.yb_timing_enable(0)
     buf = ctypes.create_string_buffer(1 << 16)
