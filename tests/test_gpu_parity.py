@@ -145,7 +145,7 @@ def test_loss_cpu_tensors_and_grad_flow(yb):
     ref = R.multiscale_loss(ref_p, tgts, ANCH, 1)
     ref[0].backward()
     for a, b in zip((total, bbox, obj, cls), ref):
-        close(a, float(b), atol=1e-7)
+        close(a, float(b.detach() if hasattr(b, "detach") else b), atol=1e-7)
     for p, q in zip(preds, ref_p):
         grad_close(p.grad, q.grad)
 
@@ -204,7 +204,7 @@ def test_loss_full_size_vs_oracle(yb):
     ref = R.multiscale_loss(ref_p, [t.cpu() for t in tg], ANCH, nc)
     ref[0].backward()
     for a, b in zip(res, ref):
-        close(a, float(b), atol=1e-7)
+        close(a, float(b.detach() if hasattr(b, "detach") else b), atol=1e-7)
     for p, q in zip(preds, ref_p):
         grad_close(p.grad, q.grad)
 

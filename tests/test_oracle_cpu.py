@@ -40,7 +40,7 @@ def test_ciou_matches_reference(golden):
     g = golden("ciou")
     p, t = T(g["pred"]).requires_grad_(True), T(g["tgt"]).requires_grad_(True)
     loss = R.ciou(p, t)
-    assert float(loss) == float(g["loss"])
+    assert float(loss.detach()) == float(g["loss"])
     loss.backward()
     torch.testing.assert_close(p.grad, T(g["gpred"]), rtol=1e-6, atol=1e-8)
     torch.testing.assert_close(t.grad, T(g["gtgt"]), rtol=1e-6, atol=1e-8)

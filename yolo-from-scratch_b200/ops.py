@@ -581,7 +581,7 @@ def build_targets(labels: Sequence, anchors_list, grid_sizes: Sequence[int], num
         if letterbox is None:
             lb = torch.tensor([[img_size, img_size, 1.0, 0.0, 0.0]] * B, dtype=torch.float64).reshape(B, 5)
         else:
-            lb = torch.as_tensor(letterbox, dtype=torch.float64).reshape(B, 5)
+            lb = torch.as_tensor(np.asarray(letterbox, dtype=np.float64)).reshape(B, 5)
         lab_d, n_d, lb_d = lab.to(dev), n_gt.to(dev), lb.to(dev)
         row = 5 + num_classes
         targets = [torch.empty(B, g, g, A, row, dtype=torch.float32, device=dev) for g in grid_sizes]
