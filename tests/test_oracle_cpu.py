@@ -62,20 +62,20 @@ def test_multiscale_loss_matches_reference(golden, name):
     preds = [T(g[f"{name}_pred{s}"]).requires_grad_(True) for s in range(3)]
     tgts = [T(g[f"{name}_tgt{s}"]) for s in range(3)]
     res = R.multiscale_loss(preds, tgts, ANCH, nc)
-    np.testing.assert_array_equal(np.array([float(r) for r in res], dtype=np.float32), g[f"{name}_losses"])
+    np.testing.assert_array_equal(np.array([float(r.detach()) for r in res], dtype=np.float32), g[f"{name}_losses"])
     res[0].backward()
     for s in range(3):
         torch.testing.assert_close(preds[s].grad, T(g[f"{name}_grad{s}"]), rtol=1e-6, atol=1e-9)
     p1 = T(g[f"{name}_pred1"]).requires_grad_(True)
     r1 = R.single_scale_loss(p1, tgts[1], ANCH[1], nc)
-    np.testing.assert_array_equal(np.array([float(r) for r in r1], dtype=np.float32), g[f"{name}_single_losses"])
+    np.testing.assert_array_equal(np.array([float(r.detach()) for r in r1], dtype=np.float32), g[f"{name}_single_losses"])
 
 
 def test_loss_without_positives(golden):
     g = golden("loss")
     preds = [T(g[f"empty_pred{s}"]) for s in range(3)]
     res = R.multiscale_loss(preds, [torch.zeros_like(p) for p in preds], ANCH, 1)
-    np.testing.assert_array_equal(np.array([float(r) for r in res], dtype=np.float32), g["empty_losses"])
+    np.testing.assert_array_equal(np.array([float(r.detach()) for r in res], dtype=np.float32), g["empty_losses"])
     assert float(res[1]) == 0.0 and float(res[3]) == 0.0 and float(res[2]) > 0.0  # tests/test_loss.py:91-109
 
 
@@ -136,7 +136,7 @@ def test_model_heads_fixture(golden):
         tgts.append(t)
     preds = [h.clone().requires_grad_(True) for h in heads]
     res = R.multiscale_loss(preds, tgts, ANCH, 1)
-    np.testing.assert_array_equal(np.array([float(r) for r in res], dtype=np.float32), g["losses"])
+    np.testing.assert_array_equal(np.array([float(r.detach()) for r in res], dtype=np.float32), g["losses"])
     res[0].backward()
     for s in range(3):
         torch.testing.assert_close(preds[s].grad[..., 4], T(g[f"grad{s}_obj"]), rtol=1e-6, atol=1e-12)

@@ -89,11 +89,15 @@ __device__ __forceinline__ int group_scale(const FilterArgs& a, uint32_t group) 
 // above 13 is re-evaluated).  On random heads the re-evaluation practically never runs, which keeps
 // the warp converged (the round-1 kernel used a window of 1.0 and spent ~80% of its instructions in
 // divergent sigmoid re-evaluations).
+// First half: one pass over the logits — maximum m, its first index mi, the runner-up m2 (largest value at any
+// other index).  The caller evaluates sigmoid(m) together with the row's other sigmoids and then calls
+// class_max_ties, which re-evaluates only when another logit can round to the same probability.
 template <typename Load>
-__device__ __forceinline__ void class_max(int nc, Load ld, float& prob, int& id) {
-    // one pass: maximum m, its first index mi, and the runner-up m2 (largest value at any other index)
-    float m = ld(0), m2 = -INFINITY;
-    int mi = 0, c = 1;
+__device__ __forceinline__ void class_max_logit(int nc, Load ld, float& m, float& m2, int& mi) {
+    m = ld(0);
+    m2 = -INFINITY;
+    mi = 0;
+    int c = 1;
     auto step = [&](float v, int idx) {
         if (v > m) { m2 = m; m = v; mi = idx; }
         else m2 = v > m2 ? v : m2;
@@ -106,18 +110,29 @@ __device__ __forceinline__ void class_max(int nc, Load ld, float& prob, int& id)
         for (int k = 0; k < 8; ++k) step(v[k], c + k);
     }
     for (; c < nc; ++c) step(ld(c), c);
-    prob = sigmoidf_ref(m);
-    id = mi;
+}
+template <typename Load>
+__device__ __forceinline__ void class_max_ties(int nc, Load ld, float m, float m2, int mi, float& prob, int& id) {
+    id = mi;   // prob = sigmoid(m) on entry
     if (m <= 5.0f && !(m2 > m - 3.1e-4f)) return;  // 2e-6*(1+e^5) < 3.1e-4: the common case without the exponential
     const float lo = (m <= 14.0f) ? m - 2e-6f * (1.0f + expf(m)) : 13.0f;
     if (!(m2 > lo)) return;  // nothing else is close enough to round to the same probability
-    for (c = 0; c < nc; ++c) {  // near-ties on either side of mi (expf need not be monotone to the last ulp)
+    for (int c = 0; c < nc; ++c) {  // near-ties on either side of mi (expf need not be monotone to the last ulp)
         const float v = ld(c);
         if (v > lo && c != mi) {
             const float p = sigmoidf_ref(v);
             if (p > prob || (p == prob && c < id)) { prob = p; id = c; }
         }
     }
+}
+
+template <typename Load>
+__device__ __forceinline__ void class_max(int nc, Load ld, float& prob, int& id) {
+    float m, m2;
+    int mi;
+    class_max_logit(nc, ld, m, m2, mi);
+    prob = sigmoidf_ref(m);
+    class_max_ties(nc, ld, m, m2, mi, prob, id);
 }
 
 // ---- bulk-async (TMA 1-D) staging ------------------------------------------------------------------
@@ -192,14 +207,26 @@ __device__ __forceinline__ void filter_emit_row(const FilterArgs& a, const Filte
     L.d_W.divmod(cell, gy, gx);
     const float aw = __ldg(L.anchors + an * 2), ah = __ldg(L.anchors + an * 2 + 1);
     const float x0 = X(0), x1r = X(1), x2r = X(2), x3r = X(3), x4r = X(4);
-    float cprob;
+    float m, m2;
+    int mi;
+    class_max_logit(a.nc, [&](int cc) { return X(5 + cc); }, m, m2, mi);
+    // the row's six sigmoids 1/(1+expf(-x)) in one basic block: expf is branch-free, the reciprocals are the
+    // division's own fast path without its range check (rcp_normal), so the six chains interleave; one check for
+    // all of them (x < -87.3: 1+e^-x >= 2^126) redoes the full divisions
+    const float d0 = 1.0f + expf(-x0), d1 = 1.0f + expf(-x1r), d2 = 1.0f + expf(-x2r), d3 = 1.0f + expf(-x3r);
+    const float d4 = 1.0f + expf(-x4r), d5 = 1.0f + expf(-m);
+    float s0 = rcp_normal(d0), s1 = rcp_normal(d1), s2 = rcp_normal(d2), s3 = rcp_normal(d3);
+    float s4 = rcp_normal(d4), cprob = rcp_normal(d5);
+    if (!(fmaxf(fmaxf(fmaxf(d0, d1), fmaxf(d2, d3)), fmaxf(d4, d5)) < kRcpNormalMax)) {
+        s0 = 1.0f / d0; s1 = 1.0f / d1; s2 = 1.0f / d2; s3 = 1.0f / d3; s4 = 1.0f / d4; cprob = 1.0f / d5;
+    }
     int cid;
-    class_max(a.nc, [&](int cc) { return X(5 + cc); }, cprob, cid);
+    class_max_ties(a.nc, [&](int cc) { return X(5 + cc); }, m, m2, mi, cprob, cid);
     // decode (:1154) with the model's img_size
-    const float bx = decode_xy(x0, (float)gx, L.inv_w);
-    const float by = decode_xy(x1r, (float)gy, L.inv_h);
-    const float bw = decode_wh(x2r, aw, a.inv_img);
-    const float bh = decode_wh(x3r, ah, a.inv_img);
+    const float bx = decode_xy_s(s0, (float)gx, L.inv_w);
+    const float by = decode_xy_s(s1, (float)gy, L.inv_h);
+    const float bw = decode_wh_s(s2, aw, a.inv_img);
+    const float bh = decode_wh_s(s3, ah, a.inv_img);
     // pixels, corners, letterbox reverse (:1192-1213)
     const float xc = bx * a.img, yc = by * a.img, wp = bw * a.img, hp = bh * a.img;
     float x1 = xc - wp * 0.5f, y1 = yc - hp * 0.5f, x2 = xc + wp * 0.5f, y2 = yc + hp * 0.5f;
@@ -208,7 +235,7 @@ __device__ __forceinline__ void filter_emit_row(const FilterArgs& a, const Filte
         x2 = (x2 - pl) * inv_s; y2 = (y2 - pt) * inv_s;
     }
     a.boxes[o] = make_float4(x1, y1, x2, y2);
-    a.scores[o] = sigmoidf_ref(x4r) * cprob;  // :1216
+    a.scores[o] = s4 * cprob;  // :1216
     a.classes[o] = (int64_t)cid;
 }
 
