@@ -906,6 +906,10 @@ def time_decode(lib, dev_sets, anchors, img, nc, n_sets, steps):
                               outs[i % 2][s].data_ptr(), B, H, W, A, row - 5, float(img), st)
     T3 = tensor_bytes(dev_sets[0][0][:1])
 
+    def box_sectors(heads):   # the backward reads only the four box logits of pred: one 32-byte sector per row (SURVEY 8d's granularity)
+        return sum(h.numel() // h.shape[-1] * min(h.shape[-1] * 4, 32) for h in heads)
+    Tb, Tb3 = box_sectors(dev_sets[0][0]), box_sectors(dev_sets[0][0][:1])
+
     def fwd_p3(i):   # the reference's call is per scale (train.py:796): the P3 head alone is the launch that carries the bytes
         h = dev_sets[i % n_sets][0][0]
         B, H, W, A, row = h.shape
@@ -917,8 +921,8 @@ def time_decode(lib, dev_sets, anchors, img, nc, n_sets, steps):
         lib.yb_decode_bwd(h.data_ptr(), anchors[0].data_ptr(), dev_sets[(i + 1) % n_sets][0][0].data_ptr(),
                           outs[i % 2][0].data_ptr(), B, H, W, A, row - 5, float(img), st)
     res = {}
-    for name, fn, nbytes in (("decode_fwd(3 scales)", fwd, 2 * T), ("decode_bwd(3 scales)", bwd, 3 * T),
-                             ("decode_fwd(P3)", fwd_p3, 2 * T3), ("decode_bwd(P3)", bwd_p3, 3 * T3)):
+    for name, fn, nbytes in (("decode_fwd(3 scales)", fwd, 2 * T), ("decode_bwd(3 scales)", bwd, 2 * T + Tb),
+                             ("decode_fwd(P3)", fwd_p3, 2 * T3), ("decode_bwd(P3)", bwd_p3, 2 * T3 + Tb3)):
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
