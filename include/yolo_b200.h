@@ -272,6 +272,14 @@ int yb_timing_collect(char* buf, size_t n);
 /* Counters for tests/bench: number of kernel launches this library has enqueued (process wide). */
 unsigned long long yb_launch_count(void);
 
+/* Self-test of the batched sigmoid (tests only; synchronises the stream).  The filter and the long-row decode
+ * evaluate the reference's 1/(1+expf(-x)) (train.py:758-759,773-774,1157; ATen's sigmoid) with the IEEE
+ * division's own fast path but without its range-check branch.  This runs both forms on the device over
+ *   [0] every float y with 2^-126 <= |y| < 2^126 : 1.0f / y against the branch-free reciprocal,
+ *   [1] every non-NaN float x whose 1+expf(-x) is inside that range : the two sigmoid forms,
+ * and writes the number of differing bit patterns to mismatches_host[0..1] (both must be 0). */
+int yb_selftest_sigmoid(unsigned long long* mismatches_host /* [2] */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

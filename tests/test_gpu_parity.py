@@ -1079,3 +1079,12 @@ def test_launch_counter_and_library(yb):
     before = lib.yb_launch_count()
     yb.decode_predictions(torch.zeros(1, 4, 4, 3, 6).cuda(), ANCH[0])
     assert lib.yb_launch_count() == before + 1
+
+
+def test_batched_sigmoid_is_bit_identical_exhaustively(yb):
+    """rcp_normal / sigmoid_ref_batch (the filter's emit and the long-row decode) against the compiler's IEEE
+    division and sigmoidf_ref over EVERY float of their domains, on the device (yb_selftest_sigmoid)."""
+    import ctypes
+    out = (ctypes.c_ulonglong * 2)(7, 7)
+    yb._lib.check(yb._lib.lib().yb_selftest_sigmoid(out, torch.cuda.current_stream().cuda_stream), "yb_selftest_sigmoid")
+    assert (int(out[0]), int(out[1])) == (0, 0)

@@ -73,6 +73,7 @@ SIGNATURES = {
     "yb_nms_graph_stats": (c_int, [c_void_p, c_size_t, c_int, c_int, POINTER(c_ulonglong), POINTER(c_ulonglong),
                                    POINTER(c_ulonglong), c_void_p]),
     "yb_eval_counts": (c_int, [POINTER(HeadsDesc), POINTER(c_void_p), c_double, c_double, c_void_p, c_void_p]),
+    "yb_selftest_sigmoid": (c_int, [POINTER(c_ulonglong), c_void_p]),
     "yb_pack_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),
 }

@@ -288,7 +288,57 @@ static int decode_launch(bool bwd, const float* pred, const float* anchors, cons
     return 0;
 }
 
+// ---- self-test of rcp_normal / sigmoid_ref_batch (yb_selftest_sigmoid) -----------------------------------------
+__global__ void __launch_bounds__(256) selftest_rcp_kernel(unsigned long long* bad) {
+    const unsigned long long n = 0xfcull << 23;   // biased exponents 1..252, either sign
+    unsigned long long mism = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < 2 * n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t bits = ((uint32_t)(i % n) + (1u << 23)) | (i >= n ? 0x80000000u : 0u);
+        const float y = __uint_as_float(bits);
+        if (__float_as_uint(1.0f / y) != __float_as_uint(rcp_normal(y))) ++mism;
+    }
+    if (mism) atomicAdd(bad, mism);
+}
+__global__ void __launch_bounds__(256) selftest_sigmoid_kernel(unsigned long long* bad) {
+    unsigned long long mism = 0;
+    for (unsigned long long i = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 4ull; i < (1ull << 32);
+         i += (unsigned long long)gridDim.x * blockDim.x * 4ull) {
+        float x[4], s[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = __uint_as_float((uint32_t)i + (uint32_t)k);
+        sigmoid_ref_batch<4>(x, s);   // includes the fallback for values outside the fast range
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x[k] == x[k] && __float_as_uint(sigmoidf_ref(x[k])) != __float_as_uint(s[k])) ++mism;
+    }
+    if (mism) atomicAdd(bad, mism);
+}
+
 }  // namespace yb
+
+extern "C" int yb_selftest_sigmoid(unsigned long long* mismatches_host, void* stream) {
+    using namespace yb;
+    YB_CHECK_ARG(mismatches_host, "selftest: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* d = nullptr;
+    YB_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long)));   // test entry point: the only allocation in the library
+    cudaError_t e = cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) {
+        selftest_rcp_kernel<<<sm_count() * 8, 256, 0, st>>>(d);
+        selftest_sigmoid_kernel<<<sm_count() * 8, 256, 0, st>>>(d + 1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mismatches_host, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        set_error("yb_selftest_sigmoid failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    count_launch(2);
+    return 0;
+}
 
 extern "C" int yb_decode_fwd(const float* pred, const float* anchors, float* out, int B, int H,
                              int W, int A, int nc, float img_size, void* stream) {
