@@ -8,7 +8,7 @@
  *
  * Conventions (all entry points):
  *   - every pointer is a CALLER-OWNED DEVICE pointer unless the name ends in `_host`;
- *     the library never allocates, frees or retains memory;
+ *     the library never allocates, frees or retains memory (the tests-only yb_selftest_sigmoid aside);
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
  *     stream); no entry point synchronises the device or the stream.  One entry point,
  *     yb_batched_nms with YB_NMS_GRAPH, additionally uses a library-owned side stream between two
